@@ -1,0 +1,170 @@
+/*
+ * scone_b200.h -- C ABI of the B200-native SCONE input-embedding lookup.
+ *
+ * This is the drop-in boundary for ONE path of llmsresearch/scone: the
+ * inference-time input-embedding lookup.  The reference has no FFI of its own
+ * (it is pure Python); each entry point below names the reference interface
+ * (file:line, relative to the upstream repository root) whose work it takes
+ * over.  The Python mirror of the reference classes (scone_b200/tokenization,
+ * scone_b200/inference) binds exactly these symbols through ctypes;
+ * INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, opaque handles; no torch / C++ types.
+ *   - every pointer named d_* is a DEVICE pointer (or a device-mapped pinned
+ *     host pointer where stated) valid on the current CUDA device.
+ *   - all work is enqueued asynchronously on `stream` (a cudaStream_t passed
+ *     as void*); buffers must stay alive until the stream is synchronised.
+ *     The only calls that synchronise are scone_index_create (one read-back of
+ *     the build audit) and scone_status_read.
+ *   - return value: 0 = OK, negative = error (SCONE_E_*); the message is
+ *     available from scone_last_error() on the calling thread.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry
+ *     point returns SCONE_E_CUDA.
+ */
+#ifndef SCONE_B200_H
+#define SCONE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCONE_B200_VERSION 100 /* 0.1.0 */
+
+/* error codes */
+#define SCONE_OK 0
+#define SCONE_E_INVALID (-1) /* bad argument */
+#define SCONE_E_CUDA (-2)    /* CUDA runtime error (incl. no device) */
+#define SCONE_E_VOCAB (-3)   /* vocabulary rejected: duplicate key, bad length, negative token */
+#define SCONE_E_NOMEM (-4)
+
+/* cache-row storage formats (formulas in oracle/py_oracle.py) */
+#define SCONE_QUANT_FP16 0 /* row = D x fp16                       (reference: `.half()`, scone/inference/engine.py:265-266) */
+#define SCONE_QUANT_INT8 1 /* row = D x int8, then 1 x fp32 scale  (per-row symmetric) */
+#define SCONE_QUANT_INT4 2 /* row = D/2 bytes (two nibbles q+8, element 2k low), then D/group x fp16 scales */
+
+/* output element types */
+#define SCONE_OUT_BF16 0
+#define SCONE_OUT_FP16 1
+#define SCONE_OUT_FP32 2 /* only for scone_table_gather (the reference's fp32 get_embeddings) */
+
+/* bits of the device status word written by scone_embed_forward */
+#define SCONE_STATUS_TOKEN_OOR 1u /* a position with no f-gram had a token id outside [0, base_rows): row zero-filled
+                                     (the reference raises IndexError from wte(), scone/models/language_model.py:239) */
+
+#define SCONE_MAX_N 7 /* longest f-gram the 32-byte slot format holds */
+
+typedef struct scone_index scone_index_t; /* opaque: device-resident f-gram index */
+
+typedef struct scone_index_info {
+    int64_t num_fgrams;
+    int64_t capacity;    /* slots */
+    int64_t bytes;       /* device bytes held by the handle */
+    int32_t max_n;
+    uint32_t len_mask;   /* bit (n-1) set when some f-gram has length n */
+    int32_t max_probe;   /* longest insert probe sequence seen at build time */
+    int32_t slot_bytes;  /* 32 */
+} scone_index_info_t;
+
+/* Where the cache rows live and how they are encoded.  Row r starts at
+ * rows + r * row_stride; payload first, scales at byte `scale_offset`. */
+typedef struct scone_table_desc {
+    const void *d_rows;   /* device pointer, or device-mapped pinned host pointer (offloaded tier) */
+    int64_t row_stride;   /* bytes; multiple of 16 */
+    int64_t num_rows;     /* N; row index = f-gram id (scone/inference/embedding_cache.py:77,99) */
+    int32_t quant;        /* SCONE_QUANT_* */
+    int32_t dim;          /* D; multiple of 8 (INT4: multiple of group) */
+    int32_t group;        /* INT4 group size (multiple of 8; 128 by default); ignored otherwise */
+    int32_t scale_offset; /* byte offset of the scale(s) inside a row; ignored for FP16 */
+} scone_table_desc_t;
+
+/* ---- library ------------------------------------------------------------- */
+int scone_version(void);
+const char *scone_last_error(void);
+
+/* ---- f-gram index ---------------------------------------------------------
+ * Replaces the Python set/dict of int tuples held by NGramExtractor
+ * (scone/tokenization/n_gram_extractor.py:41-44, filled at :96-99 / :159-165).
+ *
+ * d_tokens: int32 [n, max_n], f-gram r in row r in reading order, padded with -1.
+ * d_lens  : uint8 [n].  The id of an f-gram is its row number (frequency rank in the
+ *           reference, n_gram_extractor.py:98-99).
+ * The open-addressing table (32-byte slots, key stored inline, home slot from a
+ * rolling 64-bit hash) is built by kernels on `stream`; the call then reads back a
+ * build audit and fails with SCONE_E_VOCAB if two rows hold the same f-gram, a length
+ * is outside [1, max_n] or a token is negative.  load_factor in (0, 0.9]; <= 0 -> 0.5. */
+int scone_index_create(const int32_t *d_tokens, const uint8_t *d_lens, int64_t n, int32_t max_n,
+                       double load_factor, void *stream, scone_index_t **out);
+int scone_index_destroy(scone_index_t *index);
+int scone_index_info(const scone_index_t *index, scone_index_info_t *info);
+
+/* Longest f-gram ENDING at every position (Algorithm 2, assets/algorithm.png; the
+ * reference primitive is the membership test of n_gram_extractor.py:121-122 and the
+ * tuple->id lookup of embedding_cache.py:173).  Rows of the [B, L] batch are independent;
+ * pads are ordinary tokens (f_gram_tokenizer.py:122-123).
+ * d_ids int64 [B, L] -> d_out_id int32 [B, L] (-1 = none), d_out_len uint8 [B, L] (0 = none). */
+int scone_index_lookup(const scone_index_t *index, const int64_t *d_ids, int64_t B, int64_t L,
+                       int32_t *d_out_id, uint8_t *d_out_len, void *stream);
+
+/* d_out int32 [B, L, max_n]: id of the n-gram ending at position i (slot n-1), or -1.
+ * This is the batched form of NGramExtractor.get_token_f_grams (n_gram_extractor.py:106-126):
+ * the per-position "all f-grams containing the token" lists are a re-indexing of it. */
+int scone_index_match_all(const scone_index_t *index, const int64_t *d_ids, int64_t B, int64_t L,
+                          int32_t *d_out, void *stream);
+
+/* ---- cache table ------------------------------------------------------------
+ * Replaces EmbeddingCache's Dict[int, ndarray] / np.memmap [N, D] fp32 store
+ * (scone/inference/embedding_cache.py:49-50, :76-91). */
+
+/* Row geometry for a format: stride rounded up to `align` bytes (multiple of 16; 0 -> 32). */
+int scone_table_layout(int32_t quant, int32_t dim, int32_t group, int32_t align,
+                       int64_t *row_stride, int32_t *scale_offset);
+
+/* cache_embeddings (embedding_cache.py:56-111): quantise k fp32 rows and store them at
+ * table rows d_row_ids[0..k) (NULL -> rows row_base .. row_base+k).  d_rows_f32: float [k, D]. */
+int scone_table_store(const scone_table_desc_t *table, const float *d_rows_f32, const int64_t *d_row_ids,
+                      int64_t row_base, int64_t k, void *stream);
+
+/* get_embeddings (embedding_cache.py:113-147): out[r] = dequant(table[d_row_ids[r]]) as
+ * out_dtype ([k, D] contiguous).  Row ids outside [0, num_rows) produce a zero row and set
+ * bit SCONE_STATUS_TOKEN_OOR in *d_status when d_status is not NULL. */
+int scone_table_gather(const scone_table_desc_t *table, const int64_t *d_row_ids, int64_t k,
+                       void *d_out, int32_t out_dtype, uint32_t *d_status, void *stream);
+
+/* ---- the fused hot path -----------------------------------------------------
+ * One pass replacing, per position: get_token_f_grams + f_gram_to_id + get_embeddings
+ * + the engine's assemble loop + the wte fallback
+ * (n_gram_extractor.py:106-126, embedding_cache.py:149-181, engine.py:235-266,
+ *  language_model.py:239-243), with Algorithm-2 semantics:
+ *
+ *   out[b, i, :] = dequant(table[fgram_id[b, i]])     if an f-gram ends at (b, i)
+ *                = base_emb[ids[b, i], :]              otherwise
+ *
+ * d_base_emb : [base_rows, D] in out_dtype (bf16 / fp16), row stride D elements.
+ * d_out      : [B, L, D] out_dtype, contiguous -- the transformer's inputs_embeds layout
+ *              (language_model.py:257-258).
+ * d_pos_emb  : optional [>= L, D] in out_dtype; when not NULL, pos_emb[i] is added (fp32 add,
+ *              RNE) -- the wpe term of language_model.py:253-254.  NULL in the plain path.
+ * d_out_id / d_out_len / d_status may be NULL. */
+int scone_embed_forward(const scone_index_t *index, const scone_table_desc_t *table,
+                        const void *d_base_emb, int64_t base_rows, const void *d_pos_emb,
+                        const int64_t *d_ids, int64_t B, int64_t L,
+                        void *d_out, int32_t out_dtype,
+                        int32_t *d_out_id, uint8_t *d_out_len, uint32_t *d_status, void *stream);
+
+/* Second half only: ids already resolved (used by the sharded and staged tiers).
+ * d_fgram_id int32 [T] (-1 = fallback to base_emb[d_ids[t]]). */
+int scone_embed_gather(const scone_table_desc_t *table, const void *d_base_emb, int64_t base_rows,
+                       const void *d_pos_emb, int64_t L,
+                       const int64_t *d_ids, const int32_t *d_fgram_id, int64_t T,
+                       void *d_out, int32_t out_dtype, uint32_t *d_status, void *stream);
+
+/* Number of kernels this library has launched from the calling process (monotonic). */
+int64_t scone_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCONE_B200_H */

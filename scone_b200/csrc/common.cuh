@@ -1,0 +1,215 @@
+// common.cuh -- shared device/host helpers for libscone_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/scone_b200.h"
+
+// ---------------------------------------------------------------------------------------------
+// host side: error plumbing (no exceptions cross the C ABI)
+// ---------------------------------------------------------------------------------------------
+namespace scone {
+
+void set_error(const char *fmt, ...);
+extern std::atomic<int64_t> g_launches;
+
+#define SCONE_CUDA(expr)                                                                              \
+    do {                                                                                              \
+        cudaError_t _e = (expr);                                                                      \
+        if (_e != cudaSuccess) {                                                                      \
+            ::scone::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return SCONE_E_CUDA;                                                                      \
+        }                                                                                             \
+    } while (0)
+
+#define SCONE_REQUIRE(cond, ...)              \
+    do {                                      \
+        if (!(cond)) {                        \
+            ::scone::set_error(__VA_ARGS__);  \
+            return SCONE_E_INVALID;           \
+        }                                     \
+    } while (0)
+
+// after a <<<>>> launch
+#define SCONE_LAUNCHED()                 \
+    do {                                 \
+        ::scone::g_launches.fetch_add(1); \
+        SCONE_CUDA(cudaGetLastError());  \
+    } while (0)
+
+constexpr int kNumSMsB200 = 148;
+
+// ---------------------------------------------------------------------------------------------
+// index slot format: 32 bytes = one DRAM sector.
+//   w[0]    f-gram id, -1 = empty
+//   w[1..7] tokens in REVERSE reading order (w[1] = last token), -1 padded.  Token ids are
+//           non-negative int32, so the padding also encodes the length and equality of the seven
+//           words is exact equality of (length, tokens): no verify read, no 64-bit-hash aliasing.
+// ---------------------------------------------------------------------------------------------
+struct __align__(32) Slot {
+    int32_t w[8];
+};
+static_assert(sizeof(Slot) == 32, "slot must be one sector");
+
+struct scone_index_impl {
+    Slot *slots;
+    uint64_t cap;
+    int64_t n;
+    int32_t max_n;
+    uint32_t len_mask;
+    int32_t max_probe;
+    int device;
+};
+
+// device view passed by value to kernels
+struct IndexView {
+    const Slot *slots;
+    uint64_t cap;
+    uint32_t len_mask;
+    int32_t max_n;
+};
+
+// ---------------------------------------------------------------------------------------------
+// rolling 64-bit hash of the n-gram ENDING at a position: tokens are folded last-to-first, so
+// the hash of the (n+1)-gram is one step on from the hash of the n-gram with the same end.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint64_t hash_seed() { return 0x243F6A8885A308D3ull; }
+
+__host__ __device__ __forceinline__ uint64_t hash_roll(uint64_t h, uint32_t tok) {
+    h = (h ^ (uint64_t)tok) * 0x9E3779B97F4A7C15ull;
+    return h ^ (h >> 29);
+}
+
+__host__ __device__ __forceinline__ uint64_t hash_finish(uint64_t h, int n) {
+    h ^= (uint64_t)n * 0xD6E8FEB86659FD93ull;
+    h ^= h >> 33;
+    h *= 0xFF51AFD7ED558CCDull;
+    h ^= h >> 33;
+    h *= 0xC4CEB9FE1A85EC53ull;
+    h ^= h >> 33;
+    return h;
+}
+
+#ifdef __CUDACC__
+
+__device__ __forceinline__ uint64_t home_slot(uint64_t h, uint64_t cap) { return __umul64hi(h, cap); }
+
+// 256-bit slot load (LDG.E.256); slots are read-only while any lookup runs.
+__device__ __forceinline__ void load_slot(const Slot *p, int32_t (&w)[8]) {
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+                 : "l"(p));
+}
+
+// key[0..6]: reversed tokens, -1 padded.  Returns the f-gram id or -1.
+__device__ __forceinline__ int32_t probe(const IndexView &ix, uint64_t h, const int32_t (&key)[7]) {
+    uint64_t s = home_slot(h, ix.cap);
+    for (uint64_t it = 0; it < ix.cap; ++it) {
+        int32_t w[8];
+        load_slot(ix.slots + s, w);
+        if (w[0] < 0) return -1;
+        bool eq = true;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) eq &= (w[k + 1] == key[k]);
+        if (eq) return w[0];
+        if (++s == ix.cap) s = 0;
+    }
+    return -1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// vector memory helpers
+// ---------------------------------------------------------------------------------------------
+// streaming read of data touched once (cache rows, fallback rows): no L1 allocation
+__device__ __forceinline__ uint4 ldg_stream_16(const void *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint2 ldg_stream_8(const void *p) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.b32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint32_t ldg_stream_4(const void *p) {
+    uint32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+// write-once output: streaming (evict-first) store
+__device__ __forceinline__ void stg_stream_16(void *p, uint4 v) {
+    asm volatile("st.global.cs.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// decode of 8 consecutive elements to fp32 (exact integer -> float, then ONE fp32 multiply)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void decode_fp16x8(uint4 raw, float (&x)[8]) {
+    const __half2 *h = reinterpret_cast<const __half2 *>(&raw);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float2 f = __half22float2(h[k]);
+        x[2 * k] = f.x;
+        x[2 * k + 1] = f.y;
+    }
+}
+__device__ __forceinline__ void decode_bf16x8(uint4 raw, float (&x)[8]) {
+    const uint32_t *u = reinterpret_cast<const uint32_t *>(&raw);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        x[2 * k] = __uint_as_float(u[k] << 16);
+        x[2 * k + 1] = __uint_as_float(u[k] & 0xFFFF0000u);
+    }
+}
+// int8 -> fp32 without the I2F pipe: place (q ^ 0x80) in the low mantissa byte of 2^23 and
+// subtract 2^23 + 128; both steps are exact.
+__device__ __forceinline__ void decode_int8x8(uint2 raw, float scale, float (&x)[8]) {
+    const uint32_t w[2] = {raw.x ^ 0x80808080u, raw.y ^ 0x80808080u};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        uint32_t m = __byte_perm(w[k >> 2], 0x4B000000u, 0x7650 + (k & 3));  // bytes: [q, 0, 0, 0x4B]
+        x[k] = __fmul_rn(__uint_as_float(m) - 8388736.0f, scale);
+    }
+}
+// eight nibbles (q + 8), element 0 in the lowest nibble
+__device__ __forceinline__ void decode_int4x8(uint32_t raw, float scale, float (&x)[8]) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        uint32_t m = ((raw >> (4 * k)) & 0xFu) | 0x4B000000u;
+        x[k] = __fmul_rn(__uint_as_float(m) - 8388616.0f, scale);
+    }
+}
+
+__device__ __forceinline__ uint4 pack_bf16x8(const float (&x)[8]) {
+    uint4 r;
+    uint32_t *u = reinterpret_cast<uint32_t *>(&r);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        __nv_bfloat162 b = __floats2bfloat162_rn(x[2 * k], x[2 * k + 1]);
+        u[k] = *reinterpret_cast<uint32_t *>(&b);
+    }
+    return r;
+}
+__device__ __forceinline__ uint4 pack_fp16x8(const float (&x)[8]) {
+    uint4 r;
+    uint32_t *u = reinterpret_cast<uint32_t *>(&r);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        __half2 b = __floats2half2_rn(x[2 * k], x[2 * k + 1]);
+        u[k] = *reinterpret_cast<uint32_t *>(&b);
+    }
+    return r;
+}
+
+#endif  // __CUDACC__
+
+}  // namespace scone

@@ -1,0 +1,265 @@
+// index.cu -- the device-resident f-gram index: build, audit, longest-match lookup, match-all.
+//
+// Takes over the Python set / dict of int tuples of the reference's NGramExtractor
+// (scone/tokenization/n_gram_extractor.py:41-44, :96-99, :121-122) and the tuple -> id lookup of
+// scone/inference/embedding_cache.py:173.
+#include "common.cuh"
+#include "match.cuh"
+
+namespace scone {
+
+// audit counters read back once at create time
+struct BuildStats {
+    unsigned long long bad_len;
+    unsigned long long bad_tok;
+    unsigned long long dup;
+    unsigned int len_mask;
+    int max_probe;
+};
+
+// One thread per f-gram: claim the first free slot of its probe sequence with a CAS on the id
+// word, then fill in the key.  No lookup runs concurrently with the build.
+__global__ void __launch_bounds__(256) index_build_kernel(const int32_t *__restrict__ tokens, const uint8_t *__restrict__ lens,
+                                                          int64_t n, int32_t max_n, Slot *slots, uint64_t cap, BuildStats *stats) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int len = lens[i];
+    if (len < 1 || len > max_n) {
+        atomicAdd(&stats->bad_len, 1ull);
+        return;
+    }
+    int32_t key[7];
+    uint64_t h = hash_seed();
+    bool bad = false;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        key[k] = -1;
+        if (k < len) {
+            int32_t t = tokens[i * max_n + (len - 1 - k)];
+            bad |= t < 0;
+            key[k] = t;
+            h = hash_roll(h, (uint32_t)t);
+        }
+    }
+    if (bad) {
+        atomicAdd(&stats->bad_tok, 1ull);
+        return;
+    }
+    h = hash_finish(h, len);
+    uint64_t s = home_slot(h, cap);
+    int probes = 1;
+    for (;;) {
+        int32_t old = atomicCAS(&slots[s].w[0], -1, (int32_t)i);
+        if (old == -1) break;
+        if (++s == cap) s = 0;
+        ++probes;
+    }
+#pragma unroll
+    for (int k = 0; k < 7; ++k) slots[s].w[k + 1] = key[k];
+    atomicOr(&stats->len_mask, 1u << (len - 1));
+    atomicMax(&stats->max_probe, probes);
+}
+
+// After the build: every f-gram must find ITSELF.  Two rows with the same key resolve to the
+// same (first) slot, so the later row sees a different id -> counted as a duplicate.
+__global__ void __launch_bounds__(256) index_audit_kernel(const int32_t *__restrict__ tokens, const uint8_t *__restrict__ lens,
+                                                          int64_t n, int32_t max_n, IndexView ix, BuildStats *stats) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int len = lens[i];
+    if (len < 1 || len > max_n) return;
+    int32_t key[7];
+    uint64_t h = hash_seed();
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        key[k] = -1;
+        if (k < len) {
+            int32_t t = tokens[i * max_n + (len - 1 - k)];
+            if (t < 0) return;
+            key[k] = t;
+            h = hash_roll(h, (uint32_t)t);
+        }
+    }
+    h = hash_finish(h, len);
+    if (probe(ix, h, key) != (int32_t)i) atomicAdd(&stats->dup, 1ull);
+}
+
+// ---------------------------------------------------------------------------------------------
+// standalone match kernels (the fused path in embed.cu uses the same match_window())
+// ---------------------------------------------------------------------------------------------
+template <int P>
+__global__ void __launch_bounds__(256) lookup_kernel(IndexView ix, const int64_t *__restrict__ ids, int64_t T, int64_t L,
+                                                     int32_t *__restrict__ out_id, uint8_t *__restrict__ out_len) {
+    constexpr int G = 32 / P;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t base = warp * G;
+    if (base >= T) return;
+    WindowMatch m = match_window<P>(ix, ids, T, L, base, lane);
+    const int j = lane / P;
+    if ((lane % P) == 0 && base + j < T) {
+        if (out_id) out_id[base + j] = m.fid;
+        if (out_len) out_len[base + j] = (uint8_t)m.len;
+    }
+}
+
+template <int P>
+__global__ void __launch_bounds__(256) match_all_kernel(IndexView ix, const int64_t *__restrict__ ids, int64_t T, int64_t L,
+                                                        int32_t *__restrict__ out) {
+    constexpr int G = 32 / P;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t base = warp * G;
+    if (base >= T) return;
+    int32_t fid = candidate_id<P>(ix, ids, T, L, base, lane, /*use_len_mask=*/true);
+    const int j = lane / P, n1 = lane % P;
+    if (n1 < ix.max_n && base + j < T) out[(base + j) * ix.max_n + n1] = fid;
+}
+
+static int lanes_per_token(int max_n) { return max_n <= 1 ? 1 : max_n <= 2 ? 2 : max_n <= 4 ? 4 : 8; }
+
+}  // namespace scone
+
+using namespace scone;
+
+extern "C" {
+
+int scone_index_create(const int32_t *d_tokens, const uint8_t *d_lens, int64_t n, int32_t max_n, double load_factor,
+                       void *stream_, scone_index_t **out) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SCONE_REQUIRE(out != nullptr, "scone_index_create: out is NULL");
+    *out = nullptr;
+    SCONE_REQUIRE(n >= 0 && n < (int64_t)0x7FFFFFFF, "scone_index_create: n = %lld outside [0, 2^31-1)", (long long)n);
+    SCONE_REQUIRE(max_n >= 1 && max_n <= SCONE_MAX_N, "scone_index_create: max_n = %d outside [1, %d]", max_n, SCONE_MAX_N);
+    SCONE_REQUIRE(n == 0 || (d_tokens && d_lens), "scone_index_create: NULL vocabulary arrays");
+    if (!(load_factor > 0.0)) load_factor = 0.5;
+    SCONE_REQUIRE(load_factor <= 0.9, "scone_index_create: load_factor %.3f > 0.9", load_factor);
+
+    scone_index_impl *ix = new (std::nothrow) scone_index_impl();
+    if (!ix) {
+        set_error("scone_index_create: out of host memory");
+        return SCONE_E_NOMEM;
+    }
+    SCONE_CUDA(cudaGetDevice(&ix->device));
+    ix->n = n;
+    ix->max_n = max_n;
+    uint64_t cap = (uint64_t)((double)n / load_factor) + 1;
+    if (cap < 64) cap = 64;
+    cap = (cap + 3) & ~3ull;  // whole 128-byte lines
+    ix->cap = cap;
+    BuildStats *d_stats = nullptr;
+    BuildStats h{};
+    cudaError_t e = cudaMalloc(&ix->slots, cap * sizeof(Slot));
+    if (e == cudaSuccess) e = cudaMalloc(&d_stats, sizeof(BuildStats));
+    if (e != cudaSuccess) {
+        set_error("scone_index_create: cudaMalloc of %llu slot bytes failed: %s", (unsigned long long)(cap * sizeof(Slot)),
+                  cudaGetErrorString(e));
+        if (ix->slots) cudaFree(ix->slots);
+        delete ix;
+        return e == cudaErrorMemoryAllocation ? SCONE_E_NOMEM : SCONE_E_CUDA;
+    }
+    int rc = [&]() -> int {
+        SCONE_CUDA(cudaMemsetAsync(ix->slots, 0xFF, cap * sizeof(Slot), stream));
+        SCONE_CUDA(cudaMemsetAsync(d_stats, 0, sizeof(BuildStats), stream));
+        if (n > 0) {
+            const unsigned blocks = (unsigned)((n + 255) / 256);
+            index_build_kernel<<<blocks, 256, 0, stream>>>(d_tokens, d_lens, n, max_n, ix->slots, cap, d_stats);
+            SCONE_LAUNCHED();
+            IndexView v{ix->slots, cap, 0xFFFFFFFFu, max_n};
+            index_audit_kernel<<<blocks, 256, 0, stream>>>(d_tokens, d_lens, n, max_n, v, d_stats);
+            SCONE_LAUNCHED();
+        }
+        SCONE_CUDA(cudaMemcpyAsync(&h, d_stats, sizeof h, cudaMemcpyDeviceToHost, stream));
+        SCONE_CUDA(cudaStreamSynchronize(stream));
+        return SCONE_OK;
+    }();
+    cudaFree(d_stats);
+    if (rc == SCONE_OK && (h.bad_len || h.bad_tok || h.dup)) {
+        set_error("scone_index_create: vocabulary rejected: %llu duplicated f-grams, %llu lengths outside [1, %d], %llu rows with negative tokens",
+                  h.dup, h.bad_len, max_n, h.bad_tok);
+        rc = SCONE_E_VOCAB;
+    }
+    if (rc != SCONE_OK) {
+        cudaFree(ix->slots);
+        delete ix;
+        return rc;
+    }
+    ix->len_mask = h.len_mask;
+    ix->max_probe = h.max_probe;
+    *out = reinterpret_cast<scone_index_t *>(ix);
+    return SCONE_OK;
+}
+
+int scone_index_destroy(scone_index_t *index) {
+    if (!index) return SCONE_OK;
+    scone_index_impl *ix = reinterpret_cast<scone_index_impl *>(index);
+    cudaError_t e = cudaFree(ix->slots);
+    delete ix;
+    if (e != cudaSuccess) {
+        set_error("scone_index_destroy: cudaFree failed: %s", cudaGetErrorString(e));
+        return SCONE_E_CUDA;
+    }
+    return SCONE_OK;
+}
+
+int scone_index_info(const scone_index_t *index, scone_index_info_t *info) {
+    SCONE_REQUIRE(index && info, "scone_index_info: NULL argument");
+    const scone_index_impl *ix = reinterpret_cast<const scone_index_impl *>(index);
+    info->num_fgrams = ix->n;
+    info->capacity = (int64_t)ix->cap;
+    info->bytes = (int64_t)(ix->cap * sizeof(Slot));
+    info->max_n = ix->max_n;
+    info->len_mask = ix->len_mask;
+    info->max_probe = ix->max_probe;
+    info->slot_bytes = (int32_t)sizeof(Slot);
+    return SCONE_OK;
+}
+
+int scone_index_lookup(const scone_index_t *index, const int64_t *d_ids, int64_t B, int64_t L, int32_t *d_out_id,
+                       uint8_t *d_out_len, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SCONE_REQUIRE(index, "scone_index_lookup: NULL index");
+    SCONE_REQUIRE(B >= 0 && L >= 0, "scone_index_lookup: negative shape");
+    const int64_t T = B * L;
+    if (T == 0) return SCONE_OK;
+    SCONE_REQUIRE(d_ids, "scone_index_lookup: NULL ids");
+    SCONE_REQUIRE(T < (1ll << 40), "scone_index_lookup: batch too large");
+    const scone_index_impl *ix = reinterpret_cast<const scone_index_impl *>(index);
+    IndexView v{ix->slots, ix->cap, ix->len_mask, ix->max_n};
+    const int P = lanes_per_token(ix->max_n);
+    const int64_t windows = (T + (32 / P) - 1) / (32 / P);
+    const unsigned blocks = (unsigned)((windows + 7) / 8);
+    switch (P) {
+        case 1: lookup_kernel<1><<<blocks, 256, 0, stream>>>(v, d_ids, T, L, d_out_id, d_out_len); break;
+        case 2: lookup_kernel<2><<<blocks, 256, 0, stream>>>(v, d_ids, T, L, d_out_id, d_out_len); break;
+        case 4: lookup_kernel<4><<<blocks, 256, 0, stream>>>(v, d_ids, T, L, d_out_id, d_out_len); break;
+        default: lookup_kernel<8><<<blocks, 256, 0, stream>>>(v, d_ids, T, L, d_out_id, d_out_len); break;
+    }
+    SCONE_LAUNCHED();
+    return SCONE_OK;
+}
+
+int scone_index_match_all(const scone_index_t *index, const int64_t *d_ids, int64_t B, int64_t L, int32_t *d_out,
+                          void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SCONE_REQUIRE(index, "scone_index_match_all: NULL index");
+    SCONE_REQUIRE(B >= 0 && L >= 0, "scone_index_match_all: negative shape");
+    const int64_t T = B * L;
+    if (T == 0) return SCONE_OK;
+    SCONE_REQUIRE(d_ids && d_out, "scone_index_match_all: NULL buffer");
+    const scone_index_impl *ix = reinterpret_cast<const scone_index_impl *>(index);
+    IndexView v{ix->slots, ix->cap, ix->len_mask, ix->max_n};
+    const int P = lanes_per_token(ix->max_n);
+    const int64_t windows = (T + (32 / P) - 1) / (32 / P);
+    const unsigned blocks = (unsigned)((windows + 7) / 8);
+    switch (P) {
+        case 1: match_all_kernel<1><<<blocks, 256, 0, stream>>>(v, d_ids, T, L, d_out); break;
+        case 2: match_all_kernel<2><<<blocks, 256, 0, stream>>>(v, d_ids, T, L, d_out); break;
+        case 4: match_all_kernel<4><<<blocks, 256, 0, stream>>>(v, d_ids, T, L, d_out); break;
+        default: match_all_kernel<8><<<blocks, 256, 0, stream>>>(v, d_ids, T, L, d_out); break;
+    }
+    SCONE_LAUNCHED();
+    return SCONE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,276 @@
+"""Drop-in ``EmbeddingCache`` (mirror of reference ``scone/inference/embedding_cache.py``).
+
+Same constructor / methods as the reference class.  Rows live in a packed device table
+(FP16 / INT8 / INT4, ``scone_b200.table.CacheTable``) instead of a dict of fp32 numpy rows or an
+fp32 ``np.memmap``; ``use_memory_map=True`` (the reference's "table does not live in RAM" switch,
+:69-103) selects the offloaded tier: pinned host memory read zero-copy by the GPU.
+
+Added for the fused path: :meth:`set_base_embedding` and :meth:`lookup`, which run
+match + gather + dequant + fallback for a whole ``[B, L]`` batch in one kernel.
+"""
+
+from __future__ import annotations
+
+import os
+from collections.abc import Mapping
+from typing import Dict, List, Optional, Union
+
+import numpy as np
+import torch
+
+from ..table import CacheTable, embed_forward
+from ..tokenization.n_gram_extractor import NGramExtractor, _default_device
+
+_FORMAT = "scone_b200.cache.v1"
+
+
+class _RowsView(Mapping):
+    """``cache.embeddings``: id -> fp32 numpy row, like the reference's Dict[int, np.ndarray] (:49)."""
+
+    def __init__(self, cache: "EmbeddingCache"):
+        self._c = cache
+
+    def _ids(self) -> np.ndarray:
+        c = self._c
+        if c._present is None:
+            return np.zeros((0,), dtype=np.int64)
+        return torch.nonzero(c._present).flatten().cpu().numpy()
+
+    def __len__(self) -> int:
+        return 0 if self._c._present is None else int(self._c._present.sum().item())
+
+    def __iter__(self):
+        return iter(int(i) for i in self._ids())
+
+    def __contains__(self, key) -> bool:
+        c = self._c
+        return c._present is not None and isinstance(key, (int, np.integer)) and 0 <= int(key) < c._present.numel() \
+            and bool(c._present[int(key)].item())
+
+    def __getitem__(self, key) -> np.ndarray:
+        if key not in self:
+            raise KeyError(key)
+        return self._c._table.gather(torch.tensor([int(key)], device=self._c.device)).cpu().numpy()[0]
+
+
+class EmbeddingCache:
+    """Cache for f-gram embeddings (reference attributes: n_gram_extractor, embedding_dim, cache_dir,
+    use_memory_map, embeddings, memory_mapped_embeddings)."""
+
+    def __init__(
+        self,
+        n_gram_extractor: NGramExtractor,
+        embedding_dim: int,
+        cache_dir: Optional[str] = None,
+        use_memory_map: bool = False,
+        *,
+        quant: str = "fp16",
+        group_size: int = 128,
+        out_dtype: torch.dtype = torch.bfloat16,
+        device: Optional[torch.device] = None,
+        tier: Optional[str] = None,
+    ) -> None:
+        self.n_gram_extractor = n_gram_extractor
+        self.embedding_dim = embedding_dim
+        self.cache_dir = cache_dir
+        self.use_memory_map = use_memory_map
+        self.quant = quant
+        self.group_size = group_size
+        self.out_dtype = out_dtype
+        self.tier = tier or ("host" if use_memory_map else "hbm")
+        self._device = torch.device(device) if device is not None else None
+        self._table: Optional[CacheTable] = None
+        self._present: Optional[torch.Tensor] = None
+        self._base_emb: Optional[torch.Tensor] = None
+        self._pos_emb: Optional[torch.Tensor] = None
+        self._status: Optional[torch.Tensor] = None
+        if self.cache_dir is not None and not os.path.exists(self.cache_dir):
+            os.makedirs(self.cache_dir)
+
+    # ---- plumbing -----------------------------------------------------------------------------------
+    @property
+    def device(self) -> torch.device:
+        if self._device is None:
+            self._device = _default_device()
+        if self._device.type != "cuda":
+            raise ValueError("scone_b200 has no CPU path: device must be CUDA")
+        if self._device.index is None:
+            self._device = torch.device("cuda", torch.cuda.current_device())
+        return self._device
+
+    @property
+    def table(self) -> CacheTable:
+        if self._table is None:
+            if self.use_memory_map and self.cache_dir is None:
+                raise ValueError("Cache directory must be provided for memory mapping")     # reference :72-73
+            n = len(self.n_gram_extractor)
+            self._table = CacheTable(n, self.embedding_dim, self.quant, self.group_size, self.device, self.tier)
+            self._present = torch.zeros((n,), dtype=torch.bool, device=self.device)
+        return self._table
+
+    @property
+    def embeddings(self) -> Mapping:
+        return _RowsView(self)
+
+    @property
+    def memory_mapped_embeddings(self) -> Optional[np.ndarray]:
+        """Host-resident payload [N, D] (fp16 / int8) or [N, D/2] (int4 nibbles) when the table is offloaded."""
+        if self._table is None or self.tier != "host":
+            return None
+        st = self._table.storage.numpy()
+        D = self.embedding_dim
+        if self.quant == "fp16":
+            return st[:, :2 * D].view(np.float16)
+        if self.quant == "int8":
+            return st[:, :D].view(np.int8)
+        return st[:, :D // 2]
+
+    # ---- reference API --------------------------------------------------------------------------------
+    def cache_embeddings(self, f_gram_ids: Union[List[int], Dict[int, torch.Tensor]],
+                         embeddings: Optional[torch.Tensor] = None, verbose: bool = True) -> None:
+        """Store rows (reference :56-111).  Rows are quantised on the GPU, in chunks, straight into the table.
+
+        Accepts the reference signature ``(f_gram_ids, embeddings[k, D])`` and also the ``{id: row}`` dict
+        that the reference's own tests and scripts pass (tests/test_embedding_cache.py:78).
+        """
+        if isinstance(f_gram_ids, dict):
+            items = list(f_gram_ids.items())
+            ids = [int(k) for k, _ in items]
+            embeddings = torch.stack([torch.as_tensor(v, dtype=torch.float32).cpu() for _, v in items]) if items \
+                else torch.zeros((0, self.embedding_dim))
+        else:
+            ids = [int(i) for i in f_gram_ids]
+        if embeddings is None:
+            raise ValueError("embeddings required")
+        embeddings = torch.as_tensor(embeddings)
+        if embeddings.dim() != 2 or embeddings.shape[1] != self.embedding_dim or embeddings.shape[0] != len(ids):
+            raise ValueError(f"embeddings must be [{len(ids)}, {self.embedding_dim}]")
+        table = self.table
+        id_t = torch.tensor(ids, dtype=torch.int64, device=self.device)
+        if len(ids) and (int(id_t.min()) < 0 or int(id_t.max()) >= table.num_rows):
+            raise IndexError("f-gram id out of range")                                     # memmap backend: IndexError
+        chunk = max(1, (256 << 20) // (4 * self.embedding_dim))
+        for s in range(0, len(ids), chunk):
+            rows = embeddings[s:s + chunk].to(device=self.device, dtype=torch.float32, non_blocking=True)
+            table.store(rows, id_t[s:s + chunk])
+        self._present[id_t] = True
+
+    def get_embeddings(self, f_gram_ids: List[int], device: Optional[torch.device] = None) -> torch.Tensor:
+        """``table[ids]`` as fp32 [k, D] (reference :113-147): the stored rows, dequantised on the GPU.
+
+        Like the reference the result is a fresh fp32 tensor, left on the CPU unless ``device`` is given.
+        """
+        if self._table is None:
+            if self.use_memory_map:
+                raise ValueError("Memory-mapped embeddings not initialized")               # reference :129-130
+            if len(f_gram_ids):
+                raise KeyError(f_gram_ids[0])
+            return torch.zeros((0, self.embedding_dim))
+        ids = torch.as_tensor(list(f_gram_ids), dtype=torch.int64, device=self.device)
+        if ids.numel():
+            bad = (ids < 0) | (ids >= self._present.numel())
+            if bool(bad.any()):
+                raise (IndexError if self.use_memory_map else KeyError)(int(ids[bad][0]))
+            if not self.use_memory_map and not bool(self._present[ids].all()):
+                raise KeyError(int(ids[~self._present[ids]][0]))                           # dict backend: KeyError (:139)
+        out = self._table.gather(ids, torch.float32)
+        if device is None:
+            return out.cpu()
+        return out.to(device)
+
+    def get_token_embeddings(self, token_ids: List[int], device: Optional[torch.device] = None) -> Dict[int, torch.Tensor]:
+        """pos -> [k_pos, D] rows of all f-grams containing the position (reference :149-181); one match_all
+        launch and one gather launch for the whole sequence."""
+        token_ids = list(token_ids)
+        L = len(token_ids)
+        if L == 0 or len(self.n_gram_extractor) == 0:
+            return {}
+        index = self.n_gram_extractor.device_index(self.device)
+        ids = torch.tensor([token_ids], dtype=torch.long, device=self.device)
+        all_ids = index.match_all(ids)[0].cpu().numpy()                                    # [L, max_n]
+        per_pos: Dict[int, List[int]] = {i: [] for i in range(L)}
+        for n in range(1, min(index.max_n + 1, L + 1)):
+            for e in np.flatnonzero(all_ids[:, n - 1] >= 0):
+                for j in range(int(e) - n + 1, int(e) + 1):
+                    per_pos[j].append(int(all_ids[e, n - 1]))
+        flat = [g for i in range(L) for g in per_pos[i]]
+        if not flat:
+            return {}
+        rows = self.get_embeddings(flat, device if device is not None else None)
+        out, o = {}, 0
+        for i in range(L):
+            k = len(per_pos[i])
+            if k:
+                out[i] = rows[o:o + k]
+                o += k
+        return out
+
+    # ---- the fused path -----------------------------------------------------------------------------------
+    def set_base_embedding(self, weight: torch.Tensor, position_weight: Optional[torch.Tensor] = None) -> None:
+        """Fallback rows = the model's token embedding ``wte.weight`` [V, D] (reference language_model.py:239),
+        kept on the device in the output dtype; optional ``wpe.weight`` fuses the position add (:253-254)."""
+        if weight.dim() != 2 or weight.shape[1] != self.embedding_dim:
+            raise ValueError(f"base embedding must be [V, {self.embedding_dim}]")
+        self._base_emb = weight.detach().to(device=self.device, dtype=self.out_dtype).contiguous()
+        self._pos_emb = None if position_weight is None else \
+            position_weight.detach().to(device=self.device, dtype=self.out_dtype).contiguous()
+
+    def lookup(self, input_ids: torch.Tensor, out: Optional[torch.Tensor] = None, add_positions: bool = False):
+        """``input_ids`` long [B, L] on the GPU -> (embeds [B, L, D] out_dtype, fgram_id int32 [B, L], match_len uint8 [B, L]).
+
+        embeds[b, i] = dequant(row of the longest f-gram ending at i) or base_emb[input_ids[b, i]].
+        Asynchronous on the current stream.
+        """
+        if self._base_emb is None:
+            raise RuntimeError("call set_base_embedding(wte.weight) first: misses fall back to the token embedding")
+        if add_positions and self._pos_emb is None:
+            raise RuntimeError("add_positions=True needs set_base_embedding(..., position_weight=wpe.weight)")
+        index = self.n_gram_extractor.device_index(self.device)
+        if self._status is None:
+            self._status = torch.zeros((1,), dtype=torch.int32, device=self.device)
+        return embed_forward(index, self.table, self._base_emb, input_ids, self._pos_emb if add_positions else None, out,
+                             self._status)
+
+    def status(self) -> int:
+        """Sticky device status bits (synchronises): bit 0 = some missed token id was outside the base table."""
+        return 0 if self._status is None else int(self._status.item())
+
+    # ---- persistence (reference :183-243) ----------------------------------------------------------------------
+    def save(self, path: str) -> None:
+        """One ``.npy`` pickle like the reference, but carrying the packed table and its geometry
+        (the reference's memmap backend cannot be reloaded: raw memmap written :84-89, ``np.load`` at :232)."""
+        t = self.table
+        present = self._present.cpu().numpy()
+        np.save(path, {
+            "format": _FORMAT, "use_memory_map": self.use_memory_map, "cache_dir": self.cache_dir,
+            "embedding_dim": self.embedding_dim, "quant": self.quant, "group_size": self.group_size,
+            "row_stride": t.row_stride, "scale_offset": t.scale_offset, "num_rows": t.num_rows,
+            "storage": t.storage.cpu().numpy(), "present": present,
+        }, allow_pickle=True)
+
+    @classmethod
+    def load(cls, path: str, n_gram_extractor: NGramExtractor, cache_dir: Optional[str] = None, **kwargs) -> "EmbeddingCache":
+        """Load our format, or a dict-backend cache written by the reference (``{"embeddings": {id: fp32 row}}``)."""
+        path = str(path)
+        if not os.path.exists(path) and os.path.exists(path + ".npy"):
+            path = path + ".npy"
+        data = np.load(path, allow_pickle=True).item()
+        if data.get("format") == _FORMAT:
+            cache = cls(n_gram_extractor, data["embedding_dim"], cache_dir=cache_dir or data["cache_dir"],
+                        use_memory_map=data["use_memory_map"], quant=data["quant"], group_size=data["group_size"], **kwargs)
+            t = cache.table
+            if (t.row_stride, t.num_rows) != (data["row_stride"], data["num_rows"]):
+                raise ValueError("saved table geometry does not match this vocabulary")
+            t.storage.copy_(torch.from_numpy(data["storage"]))
+            cache._present.copy_(torch.from_numpy(data["present"]))
+            return cache
+        if data.get("use_memory_map"):
+            raise ValueError("reference memmap caches carry no rows in the .npy file; load the raw fp32 file and "
+                             "call cache_embeddings")
+        cache = cls(n_gram_extractor, data["embedding_dim"], cache_dir=cache_dir, use_memory_map=False, **kwargs)
+        emb = data["embeddings"]
+        if emb:
+            ids = sorted(emb)
+            cache.cache_embeddings(ids, torch.from_numpy(np.stack([np.asarray(emb[i], dtype=np.float32) for i in ids])),
+                                   verbose=False)
+        return cache

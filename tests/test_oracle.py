@@ -1,0 +1,223 @@
+"""CPU tests: pin the oracle (py + C) against fixtures generated from the unmodified reference."""
+
+import os
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, vocab_dict
+from oracle import py_oracle as po
+from oracle import ref_shim
+from oracle.c_oracle import COracleIndex, lib as c_lib
+
+
+def _corpus(z):
+    offs = z["corpus_offs"]
+    return [z["corpus_flat"][offs[i]:offs[i + 1]].tolist() for i in range(len(offs) - 1)]
+
+
+# ---- vocabulary construction --------------------------------------------------------------
+
+def test_kat0_fit_and_match():
+    z = load_golden("kat0.npz")
+    grams = po.fit([[1, 2, 3, 4, 1, 2, 3], [2, 3, 4, 5], [1, 2, 9]], 3, 1, 100)
+    expect = [tuple(int(t) for t in z["vocab_tokens"][i, :z["vocab_lens"][i]]) for i in range(len(z["vocab_lens"]))]
+    assert grams == expect
+    # SURVEY.md 8c KAT-0, literally
+    assert grams[:4] == [(2,), (1,), (3,), (1, 2)] and grams[17] == (1, 2, 9)
+    _, g2i, _ = po.vocab_maps(grams)
+    for fn in (po.longest_match_window, po.longest_match_direct):
+        fid, ml = fn(g2i, 3, z["query"].tolist())
+        assert fid.tolist() == [1, 3, 7, -1, 1, 3, 7, 8, 14, 15, 0, 4]
+        assert ml.tolist() == [1, 2, 3, 0, 1, 2, 3, 3, 3, 1, 1, 2]
+        assert np.array_equal(fid, z["fgram_id"]) and np.array_equal(ml, z["match_len"])
+    # truncate-THEN-filter, first-seen tie order (n_gram_extractor.py:91-94)
+    assert po.fit([[7, 8, 7, 8, 9]], 2, 2, 3) == [(7,), (8,), (7, 8)]
+
+
+def test_fit_small_matches_reference():
+    z = load_golden("fit_small.npz")
+    grams = po.fit(_corpus(z), int(z["max_n"]), int(z["min_freq"]), int(z["max_f_grams"]))
+    expect = [tuple(int(t) for t in z["vocab_tokens"][i, :z["vocab_lens"][i]]) for i in range(len(z["vocab_lens"]))]
+    assert grams == expect
+
+
+# ---- match ---------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("name", ["fit_small.npz", "vocab_n5.npz"])
+def test_longest_match_golden(name):
+    z = load_golden(name)
+    g2i = vocab_dict(z["vocab_tokens"], z["vocab_lens"])
+    max_n = int(z["max_n"])
+    for via_window in (True, False):
+        fid, ml = po.match_batch(g2i, max_n, z["query"], via_window=via_window)
+        assert np.array_equal(fid, z["fgram_id"])
+        assert np.array_equal(ml, z["match_len"])
+    cix = COracleIndex(z["vocab_tokens"], z["vocab_lens"])
+    for nt in (1, 3):
+        fid, ml = cix.match(z["query"], nthreads=nt)
+        assert np.array_equal(fid, z["fgram_id"]) and np.array_equal(ml, z["match_len"])
+    all_py = po.match_all_batch(g2i, max_n, z["query"])
+    assert np.array_equal(cix.match_all(z["query"], nthreads=2), all_py)
+    # longest = highest n present in match_all
+    has = all_py >= 0
+    ml2 = np.where(has.any(-1), max_n - np.argmax(has[..., ::-1], axis=-1), 0)
+    assert np.array_equal(ml2.astype(np.uint8), z["match_len"])
+
+
+def test_containing_lists_golden():
+    """get_token_f_grams (all f-grams containing a position, order n asc then start asc)."""
+    z = load_golden("fit_small.npz")
+    g2i = vocab_dict(z["vocab_tokens"], z["vocab_lens"])
+    for b in range(z["query"].shape[0]):
+        tf = po.token_f_grams(g2i.keys(), int(z["max_n"]), z["query"][b].tolist())
+        flat = z["cont_flat"][z["cont_flat_offs"][b]:z["cont_flat_offs"][b + 1]]
+        offs = z["cont_offs"][b]
+        for pos in range(z["query"].shape[1]):
+            assert [g2i[g] for g in tf[pos]] == flat[offs[pos]:offs[pos + 1]].tolist()
+
+
+def test_c_oracle_rejects_duplicates_and_handles_edges():
+    toks = np.array([[1, 2], [1, 2]], dtype=np.int32)
+    with pytest.raises(ValueError):
+        COracleIndex(toks, np.array([2, 2], dtype=np.uint8))
+    # same tokens, different length = different f-grams
+    cix = COracleIndex(np.array([[1, -1], [1, 1]], dtype=np.int32), np.array([1, 2], dtype=np.uint8))
+    fid, ml = cix.match(np.array([[1, 1, 1, 5]], dtype=np.int64))
+    assert fid.tolist() == [[0, 1, 1, -1]] and ml.tolist() == [[1, 2, 2, 0]]
+    # ids outside int32 never match; L = 1; empty batch
+    fid, ml = cix.match(np.array([[2 ** 40 + 1]], dtype=np.int64))
+    assert fid.tolist() == [[-1]]
+    fid, ml = cix.match(np.zeros((0, 7), dtype=np.int64))
+    assert fid.shape == (0, 7)
+    # empty vocabulary
+    e = COracleIndex(np.zeros((0, 3), dtype=np.int32), np.zeros(0, dtype=np.uint8))
+    assert e.match(np.array([[1, 2, 3]], dtype=np.int64))[0].tolist() == [[-1, -1, -1]]
+
+
+def test_fuzz_py_vs_c_oracle():
+    rng = np.random.default_rng(5)
+    for trial in range(20):
+        max_n = int(rng.integers(1, 7))
+        V = int(rng.integers(2, 30))
+        N = int(rng.integers(1, 200))
+        seen, grams = set(), []
+        for _ in range(N):
+            g = tuple(int(t) for t in rng.integers(0, V, size=int(rng.integers(1, max_n + 1))))
+            if g not in seen:
+                seen.add(g)
+                grams.append(g)
+        toks = np.full((len(grams), max_n), -1, np.int32)
+        lens = np.zeros(len(grams), np.uint8)
+        for i, g in enumerate(grams):
+            toks[i, :len(g)] = g
+            lens[i] = len(g)
+        g2i = {g: i for i, g in enumerate(grams)}
+        B, L = int(rng.integers(1, 5)), int(rng.integers(1, 40))
+        q = rng.integers(0, V, size=(B, L)).astype(np.int64)
+        a = po.match_batch(g2i, max_n, q, via_window=True)
+        b = po.match_batch(g2i, max_n, q, via_window=False)
+        c = COracleIndex(toks, lens).match(q, nthreads=2)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+        assert np.array_equal(a[0], c[0]) and np.array_equal(a[1], c[1])
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present (GPU box)")
+def test_live_reference_agrees_with_oracle():
+    """In the authoring container: run the unmodified reference side by side on fresh random input."""
+    NGramExtractor, EmbeddingCache = ref_shim.load_reference()
+    rng = np.random.default_rng(2024)
+    corpus = [((rng.zipf(1.2, size=80) - 1) % 60).tolist() for _ in range(30)]
+    ex = NGramExtractor(max_n=4, min_freq=2, max_f_grams=500).fit(corpus, verbose=False)
+    grams = po.fit(corpus, 4, 2, 500)
+    assert grams == [ex.id_to_f_gram[i] for i in range(len(grams))] and len(grams) == len(ex.f_grams)
+    q = ((rng.zipf(1.2, size=120) - 1) % 60).tolist()
+    assert po.token_f_grams(ex.f_grams, 4, q) == ex.get_token_f_grams(q)
+
+
+# ---- rows: gather, fp16 cast, quant formulas ---------------------------------------------------
+
+def test_gather_and_half_cast_golden():
+    z = load_golden("cache_small.npz")
+    tab = po.OracleTable.from_fp32(z["rows"], "fp16")
+    assert np.array_equal(z["gathered"], z["rows"][z["pick"]])          # embedding_cache.py:127-141 is a pure gather
+    bits = po.cast_bits(tab.rows_fp32(z["pick"]), "fp16")
+    assert np.array_equal(bits, z["half_bits"])                          # engine.py:265-266 `.half()`
+    assert np.array_equal(po.f32_to_f16_bits(z["gathered"]), z["half_bits"])
+
+
+def test_assemble_mean_golden():
+    z = load_golden("cache_small.npz")
+    g2i = vocab_dict(z["vocab_tokens"], z["vocab_lens"])
+    got = po.assemble_mean(g2i, int(z["max_n"]), lambda ids: z["rows"][ids], z["query"].tolist(), z["rows"].shape[1])
+    np.testing.assert_allclose(got, z["assembled"], rtol=0, atol=1e-7)
+
+
+def test_bf16_f16_casts_against_torch_and_c():
+    import torch
+    rng = np.random.default_rng(0)
+    x = np.concatenate([
+        rng.standard_normal(4000).astype(np.float32) * 0.02,
+        rng.standard_normal(2000).astype(np.float32) * 1e-6,
+        rng.standard_normal(2000).astype(np.float32) * 7e4,
+        np.array([0.0, -0.0, np.inf, -np.inf, 65504.0, 65519.99, 65520.0, 2 ** -24, 2 ** -25, 2 ** -25 * 1.0001,
+                  1.0009765625, 1.00048828125, 1.00146484375, 3.0e-5, 6.1e-5, 5.96e-8], dtype=np.float32),
+        np.arange(0, 70000, 7, dtype=np.uint32).astype(np.float32) / 1024.0,
+    ])
+    t = torch.from_numpy(x)
+    bf = t.to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
+    hf = t.to(torch.float16).view(torch.int16).numpy().view(np.uint16)
+    assert np.array_equal(po.f32_to_bf16_bits(x), bf)
+    assert np.array_equal(po.f32_to_f16_bits(x), hf)
+    L = c_lib()
+    assert np.array_equal(np.array([L.oracle_f32_to_bf16(float(v)) for v in x], dtype=np.uint16), bf)
+    assert np.array_equal(np.array([L.oracle_f32_to_f16(float(v)) for v in x], dtype=np.uint16), hf)
+    allh = np.arange(0, 65536, dtype=np.uint16)
+    finite = (allh & 0x7C00) != 0x7C00
+    back = np.array([L.oracle_f16_to_f32(int(h)) for h in allh[finite]], dtype=np.float32)
+    assert np.array_equal(back, allh[finite].view(np.float16).astype(np.float32))
+    assert np.array_equal(po.bf16_bits_to_f32(bf), t.to(torch.bfloat16).float().numpy())
+
+
+def test_quant_formulas_properties():
+    rng = np.random.default_rng(3)
+    rows = (rng.standard_normal((64, 256)) * 0.02).astype(np.float32)
+    rows[3] = 0
+    rows[5, 7] = 3.0
+    q, s = po.quant_int8_row(rows)
+    assert s[3] == 1.0 and not q[3].any()
+    assert np.abs(q).max() <= 127 and np.all(np.abs(q).max(axis=1)[np.arange(64) != 3] == 127)
+    dq = po.dequant_int8_row(q, s)
+    assert np.all(np.abs(dq - rows) <= s[:, None] * 0.5 * (1 + 1e-6))
+    p, s16 = po.quant_int4_group(rows, 128)
+    assert p.shape == (64, 128) and s16.shape == (64, 2) and s16.dtype == np.float16
+    assert np.all(s16[3] == 1.0)
+    assert ((p & 0xF) >= 1).all() and ((p >> 4) >= 1).all()              # nibble 0 (= -8) never produced
+    dq4 = po.dequant_int4_group(p, s16, 128)
+    sw = np.repeat(s16.astype(np.float32), 128, axis=1)
+    # |error| <= half a step, except where the fp16-rounded scale is below max/7 and the clamp bites
+    assert np.all(np.abs(dq4 - rows) <= sw * 0.5 * 1.01 + np.abs(rows) * 2e-3)
+    assert np.array_equal(po.unpack_int4(p)[:, 0::2], (p & 0xF).astype(np.int8) - 8)
+
+
+@pytest.mark.parametrize("quant", ["fp16", "int8", "int4"])
+@pytest.mark.parametrize("out_dtype", ["bf16", "fp16"])
+def test_embed_forward_py_vs_c(quant, out_dtype):
+    from scone_b200.utils.synthetic import pack_table_numpy
+    z = load_golden("vocab_n5.npz")
+    g2i = vocab_dict(z["vocab_tokens"], z["vocab_lens"])
+    rng = np.random.default_rng(11)
+    N, D, V = len(g2i), 256, 300
+    rows = (rng.standard_normal((N, D)) * 0.02).astype(np.float32)
+    base = po.cast_bits((rng.standard_normal((V, D)) * 0.02).astype(np.float32), out_dtype)
+    tab = po.OracleTable.from_fp32(rows, quant)
+    out, fid, ml = po.embed_forward(g2i, int(z["max_n"]), tab, base, z["query"], out_dtype)
+    assert np.array_equal(fid, z["fgram_id"]) and np.array_equal(ml, z["match_len"])
+    packed, row_stride, scale_off = pack_table_numpy(tab.quant, tab.payload, tab.scales)
+    cix = COracleIndex(z["vocab_tokens"], z["vocab_lens"])
+    scales = packed[:, scale_off:] if scale_off else None
+    cout, cid, clen, err = cix.embed(quant, D, 128, packed, row_stride, scales, row_stride, base, z["query"], out_dtype,
+                                     nthreads=2)
+    assert err == 0
+    assert np.array_equal(cid, fid) and np.array_equal(clen, ml)
+    assert np.array_equal(cout, out)
