@@ -1,0 +1,428 @@
+#!/usr/bin/env python
+"""bench.py -- tokens/s of the SCONE input-embedding lookup on B200, with roofline and CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload config2|config1|config3]
+
+One "step" = one pass of the fused hot path (longest f-gram match + row gather + dequant + fallback) over
+one [B, L] batch of synthetic token ids.  Default workload = BASELINE.json configs[1]:
+GPT-2-medium shape, 1 M f-grams, max_n = 4, INT8 cache, batch 64 x 1024, bf16 output.
+
+Printed JSON line (rank 0): `value` = whole-job tokens/s with inputs resident in HBM (K steps replayed as
+one CUDA graph, timed with CUDA events, max over ranks); `e2e` = the same metric through
+EmbeddingCache.lookup() with the ids coming from pinned HOST memory and the match result read back to the
+host every step; `roofline` = algorithmic bytes / kernel time against MEASURED_PEAKS.json; `cpu_baseline` =
+the oracle's Python port of the reference path timed on this box's cores.
+
+`--impl reference` times that CPU port alone (all cores, fork pool over batch rows) -- the reference is pure
+Python and cannot travel to the GPU box, so the port (oracle/py_oracle.py, pinned to fixtures generated from
+the unmodified reference) stands in for it.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: N f-grams, D, V, max_n, quant, B, L   (BASELINE.json configs)
+    "config1": dict(N=100_000, D=768, V=50_257, max_n=3, quant="fp16", B=8, L=512,
+                    desc="GPT-2 small, small-100k f-grams, max_n=3, FP16 cache, batch 8x512"),
+    "config2": dict(N=1_000_000, D=1024, V=50_257, max_n=4, quant="int8", B=64, L=1024,
+                    desc="GPT-2 medium, medium-1m f-grams, max_n=4, INT8 cache, batch 64x1024"),
+    "config3": dict(N=10_000_000, D=4096, V=128_000, max_n=5, quant="int4", B=256, L=2048,
+                    desc="hidden 4096, 10M f-grams, max_n=5, INT4 g128 cache, batch 256x2048"),
+}
+N_BATCHES = 8          # distinct id batches rotated through the timed steps (rows touched >> L2)
+METRIC = "tokens/sec embedded"
+
+
+def row_bytes_algorithmic(quant: str, D: int, group: int = 128) -> int:
+    return {"fp16": 2 * D, "int8": D + 4, "int4": D // 2 + 2 * D // group}[quant]
+
+
+def bytes_per_token(w, hit: float, probes: float, slot_bytes: int = 32) -> float:
+    """SURVEY.md 8d with this build's 32-byte slots: id in + probed slots + hit row / fallback row + output + (id, len) out."""
+    D = w["D"]
+    return 8 + slot_bytes * probes + hit * row_bytes_algorithmic(w["quant"], D) + (1 - hit) * 2 * D + 2 * D + 5
+
+
+def measured_peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.f, self.p = gpu_index, None, None
+
+    def __enter__(self):
+        try:
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                       "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+        return self
+
+    def __exit__(self, *a):
+        if self.p is not None:
+            self.p.terminate()
+            try:
+                self.p.wait(timeout=5)
+            except Exception:
+                self.p.kill()
+
+    def summary(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.f is None:
+            return out
+        try:
+            self.f.flush()
+            rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.count(",") >= 8]
+            os.unlink(self.f.name)
+        except Exception:
+            return out
+        sm = sorted(float(r[1]) for r in rows if r[1].strip().replace(".", "").isdigit())
+        if sm:
+            out["sm_mhz"] = sm[len(sm) // 2]
+            out["sm_max_mhz"] = float(rows[0][2])
+        out["samples"] = len(rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        out["reasons"] = [n for k, n in enumerate(names) if any("Active" in r[5 + k] and "Not" not in r[5 + k] for r in rows)]
+        return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CPU arms (the ONLY place bench.py touches oracle/)
+# ------------------------------------------------------------------------------------------------------------
+_CPU = {}
+
+
+def _cpu_rows(rows):
+    """fork-pool worker: oracle port of the reference path on some batch rows."""
+    from oracle import py_oracle as po
+    s = _CPU
+    out, fid, ml = po.embed_forward(s["g2i"], s["max_n"], s["table"], s["base_bits"], s["ids"][rows], "bf16")
+    return int(out.shape[0] * out.shape[1]), int((fid >= 0).sum())
+
+
+def cpu_setup(w, seed_rank=0):
+    """Same construction as the GPU arm (same generators, run on the CPU device) at min(N, 2M) f-grams: Python
+    dict probes are size-independent and the dict costs ~360 B / f-gram."""
+    import numpy as np
+    import torch
+    from oracle import py_oracle as po
+    from scone_b200.utils import synthetic as S
+    N = min(w["N"], 2_000_000)
+    toks, lens, longest = S.make_vocab_device(N, w["max_n"], w["V"], seed=0, device="cpu", return_longest=True)
+    ids = S.make_stream_device(toks, lens, w["B"], w["L"], w["V"], seed=100 + seed_rank, p_plant=1.0, pick_ids=longest).numpy()
+    toks, lens = toks.numpy(), lens.numpy()
+    g2i = {tuple(r[:n]): i for i, (r, n) in enumerate(zip(toks.tolist(), lens.tolist()))}
+    rng = np.random.default_rng(2)
+    # one quantised 65 536-row block tiled over the table: same footprint and gather pattern as N independent rows
+    D = w["D"]
+    blk = po.OracleTable.from_fp32(rng.standard_normal((min(N, 65536), D), dtype=np.float32) * np.float32(0.02), w["quant"])
+    reps = (N + 65535) // 65536
+    payload = np.tile(blk.payload, (reps, 1))[:N]
+    scales = None if blk.scales is None else np.tile(blk.scales, (reps,) + (1,) * (blk.scales.ndim - 1))[:N]
+    table = po.OracleTable(w["quant"], D, payload, scales)
+    base_bits = po.cast_bits(rng.standard_normal((w["V"], D), dtype=np.float32) * np.float32(0.02), "bf16")
+    _CPU.update(toks=toks, lens=lens)
+    _CPU.update(g2i=g2i, max_n=w["max_n"], table=table, base_bits=base_bits, ids=ids, N=N)
+    return N
+
+
+def cpu_time_rows(rows_per_step, cores):
+    """One CPU step over `rows_per_step` batch rows; returns (seconds, tokens)."""
+    import multiprocessing as mp
+    import numpy as np
+    B = _CPU["ids"].shape[0]
+    rows = np.arange(rows_per_step) % B
+    t0 = time.perf_counter()
+    if cores == 1:
+        tok, _ = _cpu_rows(rows)
+    else:
+        parts = [p for p in np.array_split(rows, cores) if len(p)]
+        tok = sum(t for t, _ in _CPU["pool"].map(_cpu_rows, parts))
+    return time.perf_counter() - t0, tok
+
+
+def run_reference(args, w, rank, world):
+    """--impl reference: the CPU port, all host cores, bounded sample per step."""
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    N = cpu_setup(w)
+    _CPU["pool"] = mp.get_context("fork").Pool(cores) if cores > 1 else None
+    B = w["B"]
+    # size the per-step sample so the whole run stays within ~2 minutes
+    dt, tok = cpu_time_rows(min(B, cores), cores)
+    per_row = dt / max(1, min(B, cores))
+    budget = 120.0 / max(1, args.steps + args.warmup)
+    rows_per_step = int(max(1, min(B, budget / max(per_row, 1e-9))))
+    for _ in range(args.warmup):
+        cpu_time_rows(rows_per_step, cores)
+    t_total, tok_total = 0.0, 0
+    for _ in range(args.steps):
+        dt, tok = cpu_time_rows(rows_per_step, cores)
+        t_total += dt
+        tok_total += tok
+    if _CPU["pool"] is not None:
+        _CPU["pool"].close()
+    value = tok_total / t_total
+    sample = f"{rows_per_step} of {B} batch rows x {w['L']} tokens per step; vocabulary {N} of {w['N']} f-grams (Python dict)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int8->bf16" if w["quant"] == "int8" else f"{w['quant']}->bf16", "data": "synthetic",
+        "config": {"workload": w["desc"], "batch": [w["B"], w["L"]], "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample,
+                         "what": "oracle/py_oracle.py embed_forward: dict probes n=max_n..1 + numpy gather/dequant/cast"},
+        "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------------
+
+def run_ours(args, w, rank, local_rank, world):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import scone_b200 as sb
+    from scone_b200 import _lib
+    from scone_b200.utils import synthetic as S
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- scone_b200 has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    B, L, D, N, V = w["B"], w["L"], w["D"], w["N"], w["V"]
+    T = B * L
+    # ---- build (untimed): vocabulary, index, table, fallback rows, rotating id batches -----------------------
+    toks, lens, longest = S.make_vocab_device(N, w["max_n"], V, seed=0, device=dev, return_longest=True)
+    index = sb.FGramIndex(toks, lens)
+    table = sb.CacheTable(N, D, w["quant"], device=dev)
+    S.fill_table_device(table, seed=2)
+    base = S.make_base_device(V, D, torch.bfloat16, seed=3, device=dev)
+    batches = [S.make_stream_device(toks, lens, B, L, V, seed=100 + rank * N_BATCHES + k, p_plant=1.0, pick_ids=longest)
+               for k in range(N_BATCHES)]
+    del toks, lens
+    out = torch.empty((B, L, D), dtype=torch.bfloat16, device=dev)
+    out_id = torch.empty((B, L), dtype=torch.int32, device=dev)
+    out_len = torch.empty((B, L), dtype=torch.uint8, device=dev)
+    status = torch.zeros((1,), dtype=torch.int32, device=dev)
+
+    def step(k):
+        sb.embed_forward(index, table, base, batches[k % N_BATCHES], out=out, status=status, out_id=out_id, out_len=out_len)
+
+    # hit rate / probe count of the workload (for the algorithmic byte count)
+    hits = 0
+    for k in range(N_BATCHES):
+        step(k)
+        hits += int((out_id >= 0).sum().item())
+    hit = hits / (N_BATCHES * T)
+    probes = bin(index.len_mask).count("1")
+
+    # ---- device-resident timing: K steps captured into one CUDA graph, replayed once ---------------------------
+    stream = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(stream):
+        for k in range(max(3, args.warmup)):
+            step(k)
+        stream.synchronize()
+        launches0 = _lib.launch_count()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=stream):
+            for k in range(args.steps):
+                step(k)
+        gpu_launches = _lib.launch_count() - launches0
+        graph.replay()                       # one untimed replay (graph upload)
+        stream.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        with ClockSampler(local_rank) as clocks:
+            reps = max(1, int(0.6 / max(1e-4, args.steps * 4e-5)))      # keep the GPU busy >= ~0.6 s for the clock samples
+            for _ in range(reps):
+                graph.replay()
+            stream.synchronize()
+            e0.record(stream)
+            graph.replay()
+            e1.record(stream)
+            stream.synchronize()
+            barrier()
+            ms = e0.elapsed_time(e1)
+            for _ in range(reps):
+                graph.replay()
+            stream.synchronize()
+        clk = clocks.summary()
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    assert int(status.item()) == 0
+    value = world * T * args.steps / (ms * 1e-3)
+    kernel_ms = ms / args.steps
+
+    # ---- e2e: host ids -> EmbeddingCache-level call -> match result back on the host, every step ---------------
+    h_ids = [b.cpu().pin_memory() for b in batches]
+    h_id = torch.empty((B, L), dtype=torch.int32).pin_memory()
+    h_len = torch.empty((B, L), dtype=torch.uint8).pin_memory()
+    d_ids = torch.empty((B, L), dtype=torch.int64, device=dev)
+    h_emb = torch.empty((B, L, D), dtype=torch.bfloat16).pin_memory() if args.e2e_embeds_to_host else None
+
+    def e2e_step(k, embeds_to_host=False):
+        d_ids.copy_(h_ids[k % N_BATCHES], non_blocking=True)
+        sb.embed_forward(index, table, base, d_ids, out=out, status=status, out_id=out_id, out_len=out_len)
+        h_id.copy_(out_id, non_blocking=True)
+        h_len.copy_(out_len, non_blocking=True)
+        if embeds_to_host:
+            h_emb.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()            # the caller has its results
+
+    def time_e2e(embeds_to_host):
+        for k in range(max(3, args.warmup)):
+            e2e_step(k, embeds_to_host)
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            e2e_step(k, embeds_to_host)
+        dt = time.perf_counter() - t0
+        barrier()
+        if world > 1:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return world * T * args.steps / dt
+
+    e2e_value = time_e2e(False)
+    e2e = {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": T * 8, "d2h_bytes_per_step": T * 5,
+           "note": "ids from pinned host memory; fgram_id + match_len read back to the host every step; the embeddings stay "
+                   "in HBM for the transformer, as with the reference's get_embeddings(ids, device)"}
+    if args.e2e_embeds_to_host:
+        e2e["embeds_to_host"] = {"value": time_e2e(True), "unit": "tokens/s", "d2h_bytes_per_step": T * 5 + T * D * 2}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline ---------------------------------------------------------------------------------------------
+    bpt = bytes_per_token(w, hit, probes)
+    peak, peak_src = measured_peak_hbm()
+    achieved = bpt * T / (kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "kernel": "embed_kernel (fused match+gather+dequant+fallback)",
+                "bytes_per_token": bpt, "hit_rate": hit, "probes_per_token": probes, "kernel_ms": kernel_ms}
+    prof = os.path.join(ROOT, "profiles", f"traffic_{args.workload}.json")
+    if os.path.exists(prof):
+        try:
+            roofline["traffic"] = json.load(open(prof))["dram_bytes_per_launch"]
+        except Exception:
+            pass
+
+    # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload -----------------------------------
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        Ncpu = cpu_setup(w)
+        rows = max(1, min(B, 16))
+        cpu_time_rows(1, 1)
+        dt, tok = cpu_time_rows(rows, 1)
+        cpu_baseline = {"value": tok / dt, "unit": "tokens/s", "cores": 1, "kind": "port",
+                        "sample": f"{rows} of {B} batch rows x {L} tokens; vocabulary {Ncpu} of {N} f-grams (Python dict)",
+                        "what": "oracle/py_oracle.py embed_forward (Python port of the reference path), single thread"}
+        try:
+            from oracle.c_oracle import COracleIndex
+            from scone_b200.utils.synthetic import pack_table_numpy
+            tb = _CPU["table"]
+            cix = COracleIndex(_CPU["toks"], _CPU["lens"])
+            packed, stride, soff = pack_table_numpy(w["quant"], tb.payload, tb.scales)
+            cores = os.cpu_count() or 1
+            obuf = np.empty((B, L, D), np.uint16)
+            cix.embed(w["quant"], D, 128, packed, stride, packed[:, soff:] if soff else None, stride, _CPU["base_bits"],
+                      _CPU["ids"][:1], "bf16", nthreads=1)
+            t0 = time.perf_counter()
+            cix.embed(w["quant"], D, 128, packed, stride, packed[:, soff:] if soff else None, stride, _CPU["base_bits"],
+                      _CPU["ids"], "bf16", nthreads=cores, out=obuf)
+            dtc = time.perf_counter() - t0
+            cpu_baseline["c_port"] = {"value": T / dtc, "unit": "tokens/s", "cores": cores,
+                                      "what": f"oracle/c_oracle.c, {cores} pthreads, one full batch"}
+        except Exception as e:  # the C number is informational
+            cpu_baseline["c_port"] = {"error": repr(e)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": f"{w['quant']}->bf16", "data": "synthetic",
+        "config": {"workload": w["desc"], "f_grams": N, "dim": D, "max_n": w["max_n"], "quant": w["quant"], "batch": [B, L],
+                   "per_gpu_batch": [B, L], "parallelism": f"replicas x{world} (table fits one GPU; no data-path collective)",
+                   "hit_rate": hit, "index_bytes": index.bytes, "table_bytes": table.bytes,
+                   "l2": f"inputs > L2: {N_BATCHES} rotating id batches gather rows uniformly from a {table.bytes / 1e9:.2f} GB "
+                         f"table and each step writes {T * D * 2 / 1e6:.0f} MB of output; no explicit flush",
+                   "timing": "K steps captured in one CUDA graph, CUDA events on the launching stream, max over ranks"},
+        "e2e": e2e, "gpu_launches": int(gpu_launches), "clocks": clk, "roofline": roofline,
+    }
+    if cpu_baseline is not None:
+        line["cpu_baseline"] = cpu_baseline
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-embeds-to-host", action="store_true", help="also time e2e with the embeddings copied to pinned host memory")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under it so that one process drives each GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 2000), os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, w, rank, world)
+    else:
+        run_ours(args, w, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -96,7 +96,8 @@ class CacheTable:
 
 def embed_forward(index: FGramIndex, table: CacheTable, base_emb: torch.Tensor, input_ids: torch.Tensor,
                   pos_emb: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-                  status: Optional[torch.Tensor] = None, want_ids: bool = True):
+                  status: Optional[torch.Tensor] = None, want_ids: bool = True,
+                  out_id: Optional[torch.Tensor] = None, out_len: Optional[torch.Tensor] = None):
     """The fused hot path.  Returns (embeds [B, L, D] in base_emb.dtype, fgram_id int32 [B, L], match_len uint8 [B, L]).
 
     out[b, i] = dequant(table[fgram_id[b, i]]) if an f-gram ends at (b, i) else base_emb[input_ids[b, i]]
@@ -119,8 +120,16 @@ def embed_forward(index: FGramIndex, table: CacheTable, base_emb: torch.Tensor, 
         out = torch.empty((B, L, table.dim), dtype=base_emb.dtype, device=dev)
     elif out.dtype != base_emb.dtype or tuple(out.shape) != (B, L, table.dim) or not out.is_contiguous() or out.device != dev:
         raise ValueError("out must be contiguous [B, L, D] in base_emb.dtype")
-    out_id = torch.empty((B, L), dtype=torch.int32, device=dev) if want_ids else None
-    out_len = torch.empty((B, L), dtype=torch.uint8, device=dev) if want_ids else None
+    if want_ids:
+        if out_id is None:
+            out_id = torch.empty((B, L), dtype=torch.int32, device=dev)
+        if out_len is None:
+            out_len = torch.empty((B, L), dtype=torch.uint8, device=dev)
+        if out_id.dtype != torch.int32 or out_len.dtype != torch.uint8 or out_id.numel() != B * L or out_len.numel() != B * L \
+                or not out_id.is_contiguous() or not out_len.is_contiguous() or out_id.device != dev or out_len.device != dev:
+            raise ValueError("out_id must be contiguous int32 [B, L] and out_len uint8 [B, L] on the index device")
+    else:
+        out_id = out_len = None
     with torch.cuda.device(dev):
         _lib.check(_lib.load().scone_embed_forward(
             index.handle, C.byref(table.desc), base_emb.data_ptr(), base_emb.shape[0],

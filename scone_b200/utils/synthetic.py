@@ -32,7 +32,8 @@ def zipf_like_torch(gen: torch.Generator, size, V: int, device) -> torch.Tensor:
 def make_vocab_numpy(N: int, max_n: int, V: int, seed: int = 0, min_n: int = 2, nested: bool = True) -> Tuple[np.ndarray, np.ndarray]:
     """N DISTINCT f-grams (tokens int32 [N, max_n] padded -1, lens uint8 [N]); id = generation order.
 
-    ``nested`` also inserts the (n-1)-suffix of some f-grams so that the longest-match rule is exercised.
+    ``nested`` also inserts every prefix (length >= min_n) and sometimes the (n-1)-suffix of a generated
+    f-gram, so that planted f-grams hit at most of their positions and the longest-match rule is exercised.
     Python-set de-duplication: use for N up to ~10^6.
     """
     rng = np.random.default_rng(seed)
@@ -45,55 +46,80 @@ def make_vocab_numpy(N: int, max_n: int, V: int, seed: int = 0, min_n: int = 2, 
         for i in range(m):
             g = tuple(int(t) for t in toks[i, :lens[i]])
             cands = [g]
-            if nested and len(g) - 1 >= min_n and (i & 3) == 0:
-                cands.append(g[1:])
+            if nested:
+                cands += [g[:k] for k in range(len(g) - 1, min_n - 1, -1)]
+                if len(g) - 1 >= min_n and (i & 3) == 0:
+                    cands.append(g[1:])
             for c in cands:
                 if c not in seen and len(grams) < N:
                     seen.add(c)
                     grams.append(c)
+    order = rng.permutation(N)                      # ids uncorrelated with family membership
     out = np.full((N, max_n), -1, dtype=np.int32)
     ln = np.zeros((N,), dtype=np.uint8)
     for i, g in enumerate(grams):
-        out[i, :len(g)] = g
-        ln[i] = len(g)
+        out[order[i], :len(g)] = g
+        ln[order[i]] = len(g)
     return out, ln
 
 
-def make_vocab_device(N: int, max_n: int, V: int, seed: int = 0, min_n: int = 2, device="cuda") -> Tuple[torch.Tensor, torch.Tensor]:
-    """N distinct f-grams generated on the device.  Distinct BY CONSTRUCTION: the first two tokens of f-gram i
-    encode i through a bijection of [0, V^2) (so min_n >= 2 and N <= V^2), the rest are Zipf-like."""
-    if min_n < 2 or max_n < min_n:
-        raise ValueError("device vocabulary needs 2 <= min_n <= max_n")
-    if N > V * V:
-        raise ValueError("N must be <= V^2")
+def make_vocab_device(N: int, max_n: int, V: int, seed: int = 0, device="cuda", return_longest: bool = False):
+    """N distinct f-grams generated on the device (tokens int32 [N, max_n] pad -1, lens uint8 [N]).
+
+    Families: one Zipf-like token sequence of length max_n contributes its prefixes of length 2..max_n
+    (so a planted f-gram hits at every position but its first, like text covered by frequent n-grams).
+    Distinct BY CONSTRUCTION: the first two tokens of a family encode the family number through a bijection
+    of [0, V^2).  Ids are an affine permutation of the generation order, so the rows touched by consecutive
+    positions are scattered over the whole table.  ``return_longest`` also returns the ids of the
+    length-max_n members (the ones to plant for the highest hit rate).
+    """
+    if max_n < 2:
+        raise ValueError("device vocabulary needs max_n >= 2")
+    per = max_n - 1
+    F = (N + per - 1) // per
+    if F > V * V:
+        raise ValueError("too many families for V^2 distinct token pairs")
     gen = torch.Generator(device=device)
     gen.manual_seed(seed)
-    toks = zipf_like_torch(gen, (N, max_n), V, device).to(torch.int32)
-    lens = torch.randint(min_n, max_n + 1, (N,), generator=gen, device=device, dtype=torch.int32)
+    fam = zipf_like_torch(gen, (F, max_n), V, device).to(torch.int32)
     M = V * V
     a = 0x9E3779B1 % M
     while np.gcd(a, M) != 1:
         a += 1
+    f = torch.arange(F, device=device, dtype=torch.int64)
+    x = (f * a) % M                                   # a < 2^32, f < 2^31: no overflow
+    fam[:, 0] = (x // V).to(torch.int32)
+    fam[:, 1] = (x % V).to(torch.int32)
     i = torch.arange(N, device=device, dtype=torch.int64)
-    # (i * a) mod M without overflow: a < 2^32 and i < 2^31 -> product < 2^63
-    x = (i * a) % M
-    toks[:, 0] = (x // V).to(torch.int32)
-    toks[:, 1] = (x % V).to(torch.int32)
+    b = 0x85EBCA6B % max(N, 1)
+    while np.gcd(b, max(N, 1)) != 1:
+        b += 1
+    ids = (i * b + 12345) % N                         # affine bijection of [0, N)
+    lens_gen = (2 + (i % per)).to(torch.int32)
+    toks_gen = fam[i // per]
     k = torch.arange(max_n, device=device, dtype=torch.int32)[None, :]
-    toks = torch.where(k < lens[:, None], toks, torch.full_like(toks, -1))
-    return toks.contiguous(), lens.to(torch.uint8)
+    toks_gen = torch.where(k < lens_gen[:, None], toks_gen, torch.full_like(toks_gen, -1))
+    toks = torch.empty_like(toks_gen)
+    lens = torch.empty((N,), dtype=torch.uint8, device=device)
+    toks[ids] = toks_gen
+    lens[ids] = lens_gen.to(torch.uint8)
+    if return_longest:
+        return toks.contiguous(), lens, ids[lens_gen == max_n].contiguous()
+    return toks.contiguous(), lens
 
 
 # ---- token streams -----------------------------------------------------------------------------------------------------
 
 def make_stream_numpy(vocab_tokens: np.ndarray, vocab_lens: np.ndarray, B: int, L: int, V: int, seed: int = 1,
-                      p_plant: float = 0.8) -> np.ndarray:
+                      p_plant: float = 0.8, pick_ids: Optional[np.ndarray] = None) -> np.ndarray:
+    """[B, L] int64 stream of pieces: with probability p_plant a whole vocabulary f-gram (id uniform over
+    ``pick_ids`` or the whole vocabulary), else one Zipf-like token.  Pieces may straddle row ends."""
     rng = np.random.default_rng(seed)
     T, N, max_n = B * L, len(vocab_lens), vocab_tokens.shape[1]
     out = zipf_like_numpy(rng, T + max_n, V)
     if N:
         planted = rng.random(T) < p_plant
-        pick = rng.integers(0, N, size=T)
+        pick = rng.integers(0, N, size=T) if pick_ids is None else np.asarray(pick_ids)[rng.integers(0, len(pick_ids), size=T)]
         plen = np.where(planted, vocab_lens[pick].astype(np.int64), 1)
         off = np.cumsum(plen) - plen
         keep = off < T
@@ -104,7 +130,7 @@ def make_stream_numpy(vocab_tokens: np.ndarray, vocab_lens: np.ndarray, B: int, 
 
 
 def make_stream_device(vocab_tokens: torch.Tensor, vocab_lens: torch.Tensor, B: int, L: int, V: int, seed: int = 1,
-                       p_plant: float = 0.8) -> torch.Tensor:
+                       p_plant: float = 0.8, pick_ids: Optional[torch.Tensor] = None) -> torch.Tensor:
     device = vocab_tokens.device
     gen = torch.Generator(device=device)
     gen.manual_seed(seed)
@@ -113,6 +139,8 @@ def make_stream_device(vocab_tokens: torch.Tensor, vocab_lens: torch.Tensor, B: 
     if N:
         planted = torch.rand((T,), generator=gen, device=device) < p_plant
         pick = torch.randint(0, N, (T,), generator=gen, device=device)
+        if pick_ids is not None:
+            pick = pick_ids[torch.randint(0, pick_ids.numel(), (T,), generator=gen, device=device)]
         plen = torch.where(planted, vocab_lens[pick].to(torch.int64), torch.ones_like(pick))
         off = torch.cumsum(plen, 0) - plen
         keep = off < T

@@ -1,0 +1,406 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle, bit-exact.
+
+Bars (BASELINE.json north_star): f-gram ids and match lengths bit-exact; embeddings within 1 ulp
+(bf16 / fp16) of the pinned dequant formula -- here they are in fact required to be bit-identical,
+with the 1-ulp bound asserted first so a failure says which bar broke.
+"""
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, vocab_dict
+from oracle import py_oracle as po
+from oracle.c_oracle import COracleIndex
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _mods():
+    import scone_b200
+    from scone_b200.utils import synthetic
+    return scone_b200, synthetic
+
+
+def _index(toks, lens, **kw):
+    sb, _ = _mods()
+    return sb.FGramIndex(torch.from_numpy(np.ascontiguousarray(toks, dtype=np.int32)).to(DEV),
+                         torch.from_numpy(np.ascontiguousarray(lens, dtype=np.uint8)).to(DEV), **kw)
+
+
+def _bits(t: torch.Tensor) -> np.ndarray:
+    return t.contiguous().view(torch.int16).cpu().numpy().view(np.uint16)
+
+
+def _from_bits(b: np.ndarray, dtype) -> torch.Tensor:
+    return torch.from_numpy(b.view(np.int16).copy()).view(dtype).to(DEV)
+
+
+TORCH_DT = {"bf16": torch.bfloat16, "fp16": torch.float16}
+
+
+def test_library_is_native_and_loaded():
+    from scone_b200 import _lib
+    L = _lib.load()
+    assert L.scone_version() == 100
+    before = _lib.launch_count()
+    ix = _index(np.array([[1, 2]], np.int32), np.array([2], np.uint8))
+    ix.lookup(torch.tensor([[1, 2, 3]], device=DEV))
+    torch.cuda.synchronize()
+    assert _lib.launch_count() >= before + 3          # build + audit + lookup kernels really launched
+
+
+# ---- match -------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("name", ["kat0.npz", "fit_small.npz", "vocab_n5.npz", "cache_small.npz"])
+def test_lookup_golden(name):
+    z = load_golden(name)
+    ix = _index(z["vocab_tokens"], z["vocab_lens"])
+    q = z["query"]
+    q2 = q[None, :] if q.ndim == 1 else q
+    fid, ml = ix.lookup(torch.from_numpy(q2).to(DEV))
+    assert np.array_equal(fid.cpu().numpy().reshape(q.shape), z["fgram_id"])
+    assert np.array_equal(ml.cpu().numpy().reshape(q.shape), z["match_len"])
+    g2i = vocab_dict(z["vocab_tokens"], z["vocab_lens"])
+    allm = ix.match_all(torch.from_numpy(q2).to(DEV)).cpu().numpy()
+    assert np.array_equal(allm, po.match_all_batch(g2i, z["vocab_tokens"].shape[1], q2))
+
+
+def test_kat0_literal():
+    """SURVEY.md 8c KAT-0 spelled out."""
+    sb, _ = _mods()
+    ex = sb.NGramExtractor(max_n=3, min_freq=1, max_f_grams=100).fit([[1, 2, 3, 4, 1, 2, 3], [2, 3, 4, 5], [1, 2, 9]], verbose=False)
+    assert ex.id_to_f_gram[0] == (2,) and ex.id_to_f_gram[7] == (1, 2, 3) and ex.id_to_f_gram[17] == (1, 2, 9)
+    fid, ml = ex.lookup(torch.tensor([[1, 2, 3, 7, 1, 2, 3, 4, 5, 9, 2, 3]], device=DEV))
+    assert fid[0].tolist() == [1, 3, 7, -1, 1, 3, 7, 8, 14, 15, 0, 4]
+    assert ml[0].tolist() == [1, 2, 3, 0, 1, 2, 3, 3, 3, 1, 1, 2]
+    ex2 = sb.NGramExtractor(max_n=2, min_freq=2, max_f_grams=3).fit([[7, 8, 7, 8, 9]], verbose=False)
+    assert ex2.f_gram_to_id == {(7,): 0, (8,): 1, (7, 8): 2}
+
+
+def test_index_build_audit():
+    with pytest.raises(ValueError, match="duplicated"):
+        _index(np.array([[1, 2], [3, 4], [1, 2]], np.int32), np.array([2, 2, 2], np.uint8))
+    with pytest.raises(ValueError, match="lengths"):
+        _index(np.array([[1, 2]], np.int32), np.array([3], np.uint8))
+    with pytest.raises(ValueError, match="negative"):
+        _index(np.array([[1, -1]], np.int32), np.array([2], np.uint8))
+    with pytest.raises(ValueError, match="max_n"):
+        _index(np.zeros((1, 8), np.int32), np.array([8], np.uint8))
+    # same tokens, different length = different keys; empty vocabulary; load factors
+    ix = _index(np.array([[1, -1], [1, 1]], np.int32), np.array([1, 2], np.uint8))
+    fid, ml = ix.lookup(torch.tensor([[1, 1, 1, 5]], device=DEV))
+    assert fid.tolist() == [[0, 1, 1, -1]] and ml.tolist() == [[1, 2, 2, 0]]
+    e = _index(np.zeros((0, 3), np.int32), np.zeros((0,), np.uint8))
+    assert e.lookup(torch.tensor([[1, 2, 3]], device=DEV))[0].tolist() == [[-1, -1, -1]]
+    assert e.len_mask == 0
+
+
+def test_lookup_edge_shapes_and_ids():
+    _, S = _mods()
+    toks, lens = S.make_vocab_numpy(500, 5, 60, seed=4, min_n=1)
+    cix = COracleIndex(toks, lens)
+    for lf in (0.25, 0.5, 0.9):
+        ix = _index(toks, lens, load_factor=lf)
+        for (B, L) in [(1, 1), (1, 2), (3, 5), (7, 33), (2, 257), (1, 4096), (33, 1)]:
+            q = S.make_stream_numpy(toks, lens, B, L, 60, seed=B * 1000 + L)
+            fid, ml = ix.lookup(torch.from_numpy(q).to(DEV))
+            rid, rl = cix.match(q)
+            assert np.array_equal(fid.cpu().numpy(), rid) and np.array_equal(ml.cpu().numpy(), rl), (lf, B, L)
+    # token ids outside int32 / negative: never match, never crash
+    q = np.array([[5, 2 ** 40 + 5, -7, 5, 5]], dtype=np.int64)
+    fid, ml = ix.lookup(torch.from_numpy(q).to(DEV))
+    rid, rl = cix.match(q)
+    assert np.array_equal(fid.cpu().numpy(), rid) and np.array_equal(ml.cpu().numpy(), rl)
+    # empty batch
+    fid, ml = ix.lookup(torch.zeros((0, 9), dtype=torch.long, device=DEV))
+    assert fid.shape == (0, 9)
+    with pytest.raises(ValueError):
+        ix.lookup(torch.zeros((2, 2), dtype=torch.long))          # CPU tensor: no CPU path
+
+
+@pytest.mark.parametrize("max_n", [1, 2, 3, 4, 5, 6, 7])
+def test_lookup_all_max_n(max_n):
+    _, S = _mods()
+    toks, lens = S.make_vocab_numpy(3000, max_n, 40, seed=max_n, min_n=1)
+    ix = _index(toks, lens)
+    q = S.make_stream_numpy(toks, lens, 5, 301, 40, seed=9)
+    fid, ml = ix.lookup(torch.from_numpy(q).to(DEV))
+    rid, rl = COracleIndex(toks, lens).match(q)
+    assert np.array_equal(fid.cpu().numpy(), rid) and np.array_equal(ml.cpu().numpy(), rl)
+    assert (rl == max_n).any()
+
+
+# ---- table formats ---------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("quant", ["fp16", "int8", "int4"])
+@pytest.mark.parametrize("D", [128, 768, 1024])
+def test_table_store_is_bit_identical_to_oracle_quantiser(quant, D):
+    sb, S = _mods()
+    rows = S.make_rows_numpy(300, D, seed=D)
+    rows[3] = 0.0
+    rows[5, 7] = 3.0
+    rows[6] *= 1e-7            # int4: scale underflows fp16 -> scale 1
+    rows[7] *= 1e4
+    tab = po.OracleTable.from_fp32(rows, quant)
+    packed, stride, soff = S.pack_table_numpy(quant, tab.payload, tab.scales)
+    t = sb.CacheTable(300, D, quant)
+    assert (t.row_stride, t.scale_offset) == (stride, soff)
+    perm = np.random.default_rng(0).permutation(300)
+    t.store(torch.from_numpy(rows[perm]).to(DEV), torch.from_numpy(perm).to(DEV))
+    assert np.array_equal(t.storage.cpu().numpy(), packed)
+    # dequantising gather == oracle dequant, exactly, in fp32 and in both 16-bit types
+    pick = np.array([0, 299, 3, 5, 5, 6, 7, 17], dtype=np.int64)
+    got = t.gather(torch.from_numpy(pick).to(DEV)).cpu().numpy()
+    assert np.array_equal(got, tab.rows_fp32(pick))
+    for name, dt in TORCH_DT.items():
+        got16 = _bits(t.gather(torch.from_numpy(pick).to(DEV), dt))
+        assert np.array_equal(got16, po.cast_bits(tab.rows_fp32(pick), name))
+
+
+# ---- the fused path ------------------------------------------------------------------------------------------------
+
+def _embed_case(quant, out_dtype, D, max_n, N, V, B, L, seed, min_n=2, p_plant=0.7, with_pos=False):
+    sb, S = _mods()
+    toks, lens = S.make_vocab_numpy(N, max_n, V, seed=seed, min_n=min_n)
+    q = S.make_stream_numpy(toks, lens, B, L, V, seed=seed + 1, p_plant=p_plant)
+    rows = S.make_rows_numpy(N, D, seed=seed + 2)
+    base_bits = po.cast_bits(S.make_rows_numpy(V, D, seed=seed + 3), out_dtype)
+    tab = po.OracleTable.from_fp32(rows, quant)
+    packed, stride, soff = S.pack_table_numpy(quant, tab.payload, tab.scales)
+    cix = COracleIndex(toks, lens)
+    want, wid, wlen, err = cix.embed(quant, D, 128, packed, stride, packed[:, soff:] if soff else None, stride, base_bits, q,
+                                     out_dtype, nthreads=4)
+    assert err == 0
+    ix = _index(toks, lens)
+    t = sb.CacheTable(N, D, quant)
+    t.store(torch.from_numpy(rows).to(DEV))
+    base = _from_bits(base_bits, TORCH_DT[out_dtype])
+    status = torch.zeros(1, dtype=torch.int32, device=DEV)
+    out, fid, ml = sb.embed_forward(ix, t, base, torch.from_numpy(q).to(DEV), status=status)
+    torch.cuda.synchronize()
+    assert np.array_equal(fid.cpu().numpy(), wid), "f-gram ids must be bit-exact"
+    assert np.array_equal(ml.cpu().numpy(), wlen), "match lengths must be bit-exact"
+    got = _bits(out)
+    assert po.ulp_distance(got, want).max() <= 1, "embeddings must be within 1 ulp"
+    assert np.array_equal(got, want)
+    assert int(status.item()) == 0
+    return dict(toks=toks, lens=lens, q=q, tab=tab, base_bits=base_bits, want=want, wid=wid, hit=float((wid >= 0).mean()))
+
+
+@pytest.mark.parametrize("quant", ["fp16", "int8", "int4"])
+@pytest.mark.parametrize("out_dtype", ["bf16", "fp16"])
+@pytest.mark.parametrize("D,max_n", [(128, 3), (768, 3), (1024, 4), (4096, 5), (2048, 7), (8, 1), (136, 2)])
+def test_embed_forward_matches_oracle(quant, out_dtype, D, max_n):
+    if quant == "int4" and D % 128:
+        pytest.skip("INT4 needs D % group == 0")
+    r = _embed_case(quant, out_dtype, D, max_n, N=2000, V=500, B=3, L=211, seed=D + max_n, min_n=1 if max_n < 3 else 2)
+    assert 0.2 < r["hit"] < 1.0            # both branches exercised
+
+
+def test_embed_forward_python_oracle_config1_shape():
+    """BASELINE config 1 in full against the PYTHON oracle (the reference-pinned one): D = 768, max_n = 3,
+    FP16 table, batch 8 x 512; vocabulary 100 000 f-grams."""
+    sb, S = _mods()
+    N, D, V, max_n, B, L = 100_000, 768, 50_257, 3, 8, 512
+    toks, lens = S.make_vocab_numpy(N, max_n, V, seed=0, min_n=1)
+    q = S.make_stream_numpy(toks, lens, B, L, V, seed=1)
+    rows = S.make_rows_numpy(N, D, seed=2)
+    base_bits = po.cast_bits(S.make_rows_numpy(V, D, seed=3), "bf16")
+    g2i = vocab_dict(toks, lens)
+    want, wid, wlen = po.embed_forward(g2i, max_n, po.OracleTable.from_fp32(rows, "fp16"), base_bits, q, "bf16")
+    # the window form of the reference primitive on a sample of rows
+    w2, l2 = po.match_batch(g2i, max_n, q[:2], via_window=True)
+    assert np.array_equal(w2, wid[:2]) and np.array_equal(l2, wlen[:2])
+    ex = sb.NGramExtractor.from_arrays(toks, lens)
+    cache = sb.EmbeddingCache(ex, D, quant="fp16", out_dtype=torch.bfloat16)
+    cache.cache_embeddings(list(range(N)), torch.from_numpy(rows), verbose=False)
+    cache.set_base_embedding(_from_bits(base_bits, torch.bfloat16))
+    out, fid, ml = cache.lookup(torch.from_numpy(q).to(DEV))
+    assert np.array_equal(fid.cpu().numpy(), wid) and np.array_equal(ml.cpu().numpy(), wlen)
+    assert np.array_equal(_bits(out), want)
+    assert cache.status() == 0
+    assert (wid >= 0).mean() > 0.5
+
+
+def test_embed_forward_status_and_fallback_edges():
+    sb, S = _mods()
+    toks, lens = S.make_vocab_numpy(100, 3, 50, seed=1)
+    ix = _index(toks, lens)
+    t = sb.CacheTable(100, 64, "int8")
+    t.store(torch.from_numpy(S.make_rows_numpy(100, 64)).to(DEV))
+    base = torch.randn(50, 64, device=DEV).to(torch.bfloat16)
+    status = torch.zeros(1, dtype=torch.int32, device=DEV)
+    q = torch.tensor([[49, 50, 7, -1, 3]], device=DEV)       # 50 and -1 are outside the base table
+    out, fid, ml = sb.embed_forward(ix, t, base, q, status=status)
+    assert int(status.item()) == 1
+    miss = (fid[0] < 0).cpu().numpy()
+    assert miss[1] and miss[3]
+    assert not out[0, 1].any() and not out[0, 3].any()         # zero rows, flagged
+    assert torch.equal(out[0, 0], base[49]) or not miss[0]
+    # empty batch, wrong device / dtype
+    o, f, m = sb.embed_forward(ix, t, base, torch.zeros((0, 4), dtype=torch.long, device=DEV))
+    assert o.shape == (0, 4, 64)
+    with pytest.raises(ValueError):
+        sb.embed_forward(ix, t, base.float(), q)
+    with pytest.raises(ValueError):
+        sb.embed_forward(ix, t, base, q.cpu())
+
+
+def test_embed_forward_with_positions():
+    """Fused wpe add (language_model.py:253-254): fp32 add of the two 16-bit values, RNE."""
+    sb, S = _mods()
+    r = _embed_case("int8", "bf16", 256, 4, N=1000, V=300, B=4, L=97, seed=21)
+    ix = _index(r["toks"], r["lens"])
+    t = sb.CacheTable(1000, 256, "int8")
+    t.store(torch.from_numpy(S.make_rows_numpy(1000, 256, seed=23)).to(DEV))
+    base = _from_bits(r["base_bits"], torch.bfloat16)
+    pos_bits = po.cast_bits(S.make_rows_numpy(128, 256, seed=5), "bf16")
+    out, fid, ml = sb.embed_forward(ix, t, base, torch.from_numpy(r["q"]).to(DEV), pos_emb=_from_bits(pos_bits, torch.bfloat16))
+    x = po.bf16_bits_to_f32(r["want"]) + po.bf16_bits_to_f32(pos_bits)[None, :97, :]
+    assert np.array_equal(_bits(out), po.f32_to_bf16_bits(x.astype(np.float32)))
+
+
+def test_embed_gather_resolved_ids():
+    sb, S = _mods()
+    r = _embed_case("int4", "fp16", 512, 5, N=1500, V=400, B=2, L=300, seed=31)
+    t = sb.CacheTable(1500, 512, "int4")
+    t.store(torch.from_numpy(S.make_rows_numpy(1500, 512, seed=33)).to(DEV))
+    base = _from_bits(r["base_bits"], torch.float16)
+    out = sb.embed_gather(t, base, torch.from_numpy(r["q"]).to(DEV), torch.from_numpy(r["wid"]).to(DEV))
+    assert np.array_equal(_bits(out), r["want"])
+
+
+# ---- full BASELINE sizes: C oracle on everything + size-independent properties -------------------------------------
+
+def test_config2_full_size_against_c_oracle():
+    """BASELINE config 2: D = 1024, 1 M f-grams, max_n = 4, INT8, batch 64 x 1024."""
+    sb, S = _mods()
+    N, D, V, max_n, B, L = 1_000_000, 1024, 50_257, 4, 64, 1024
+    toks_d, lens_d = S.make_vocab_device(N, max_n, V, seed=0, device=DEV)
+    ix = sb.FGramIndex(toks_d, lens_d)
+    q_d = S.make_stream_device(toks_d, lens_d, B, L, V, seed=1)
+    t = sb.CacheTable(N, D, "int8")
+    S.fill_table_device(t, seed=2)
+    base = S.make_base_device(V, D, torch.bfloat16, seed=3, device=DEV)
+    out, fid, ml = sb.embed_forward(ix, t, base, q_d)
+    torch.cuda.synchronize()
+    toks, lens, q = toks_d.cpu().numpy(), lens_d.cpu().numpy(), q_d.cpu().numpy()
+    cix = COracleIndex(toks, lens)
+    packed = t.storage.cpu().numpy()
+    want, wid, wlen, err = cix.embed("int8", D, 128, packed, t.row_stride, packed[:, t.scale_offset:], t.row_stride,
+                                     _bits(base), q, "bf16", nthreads=8)
+    assert err == 0
+    assert np.array_equal(fid.cpu().numpy(), wid) and np.array_equal(ml.cpu().numpy(), wlen)
+    assert np.array_equal(_bits(out), want)
+    hit = wid >= 0
+    assert 0.6 < hit.mean() < 1.0
+    # properties that do not depend on the oracle:
+    #  (1) a hit row dequantises to the table row it names; a miss row IS the base row
+    assert torch.equal(out[torch.from_numpy(~hit).to(DEV)], base[q_d[torch.from_numpy(~hit).to(DEV)]])
+    sel = torch.from_numpy(np.flatnonzero(hit.ravel())[:4096]).to(DEV)
+    assert torch.equal(out.view(-1, D)[sel], t.gather(fid.view(-1)[sel].long(), torch.bfloat16))
+    #  (2) the matched f-gram really is the suffix of the window, and no longer f-gram of the vocabulary was planted there
+    ids_flat, wl = q.reshape(-1), wlen.reshape(-1)
+    for tpos in np.flatnonzero(hit.ravel())[:2000]:
+        n = int(wl[tpos])
+        assert np.array_equal(toks[wid.ravel()[tpos], :n], ids_flat[tpos - n + 1:tpos + 1])
+    #  (3) idempotence / determinism: a second launch gives identical bits
+    out2, fid2, _ = sb.embed_forward(ix, t, base, q_d)
+    assert torch.equal(out, out2) and torch.equal(fid, fid2)
+    #  (4) row independence: shuffling batch rows shuffles outputs
+    perm = torch.randperm(B, device=DEV)
+    out3, _, _ = sb.embed_forward(ix, t, base, q_d[perm].contiguous())
+    assert torch.equal(out3, out[perm])
+
+
+# ---- drop-in classes (the reference's own tests, on integer ids) -------------------------------------------------------
+
+def test_dropin_get_token_f_grams_golden():
+    sb, _ = _mods()
+    z = load_golden("fit_small.npz")
+    ex = sb.NGramExtractor.from_arrays(z["vocab_tokens"], z["vocab_lens"])
+    g2i = ex.f_gram_to_id
+    for b in range(z["query"].shape[0]):
+        tf = ex.get_token_f_grams(z["query"][b].tolist())
+        flat = z["cont_flat"][z["cont_flat_offs"][b]:z["cont_flat_offs"][b + 1]]
+        offs = z["cont_offs"][b]
+        for pos in range(z["query"].shape[1]):
+            assert [g2i[g] for g in tf[pos]] == flat[offs[pos]:offs[pos + 1]].tolist()
+
+
+def test_dropin_embedding_cache_like_reference_tests(tmp_path):
+    """tests/test_embedding_cache.py of the reference, on the golden cache fixture."""
+    sb, _ = _mods()
+    z = load_golden("cache_small.npz")
+    ex = sb.NGramExtractor.from_arrays(z["vocab_tokens"], z["vocab_lens"])
+    N, D = z["rows"].shape
+    cache = sb.EmbeddingCache(n_gram_extractor=ex, embedding_dim=D, cache_dir=str(tmp_path / "cache"))
+    assert cache.n_gram_extractor is ex and cache.embedding_dim == D
+    assert cache.embeddings == {} and cache.memory_mapped_embeddings is None           # :66-72
+    rows = torch.from_numpy(z["rows"])
+    cache.cache_embeddings({i: rows[i] for i in range(N)})                               # dict form, :75-86
+    assert len(cache.embeddings) == N and 5 in cache.embeddings
+    got = cache.get_embeddings(z["pick"].tolist())                                      # :89-101
+    assert got.dtype == torch.float32 and got.device.type == "cpu"
+    assert torch.equal(got, torch.from_numpy(z["gathered"]).half().float())             # stored as fp16 (RNE)
+    assert torch.allclose(got, torch.from_numpy(z["gathered"]), rtol=1e-3, atol=1e-6)
+    assert np.array_equal(got.half().view(torch.int16).numpy().view(np.uint16), z["half_bits"])   # engine.py:265-266
+    te = cache.get_token_embeddings(z["query"].tolist())                                # :104-117, with values
+    assert sorted(te) == z["te_pos"].tolist()
+    assert [te[int(p)].shape[0] for p in z["te_pos"]] == z["te_cnt"].tolist()
+    assert torch.equal(torch.cat([te[int(p)] for p in z["te_pos"]]), torch.from_numpy(z["te_rows"]).half().float())
+    with pytest.raises(KeyError):
+        sb.EmbeddingCache(ex, D).get_embeddings([0])
+    path = tmp_path / "embeddings.cache"
+    cache.save(str(path))                                                               # :120-143
+    loaded = sb.EmbeddingCache.load(str(path), n_gram_extractor=ex, cache_dir=cache.cache_dir)
+    assert len(loaded.embeddings) == N
+    assert torch.equal(loaded.get_embeddings(z["pick"].tolist()), got)
+    # memory-mapped flavour = offloaded (pinned host) tier, :146-194
+    mm = sb.EmbeddingCache(ex, D, cache_dir=str(tmp_path / "cache"), use_memory_map=True)
+    with pytest.raises(ValueError):
+        sb.EmbeddingCache(ex, D, use_memory_map=True).cache_embeddings([0], rows[:1])
+    mm.cache_embeddings(list(range(N)), rows, verbose=False)
+    assert isinstance(mm.memory_mapped_embeddings, np.ndarray) and mm.memory_mapped_embeddings.shape == (N, D)
+    assert torch.equal(mm.get_embeddings(z["pick"].tolist()), got)
+    mm.set_base_embedding(torch.zeros(64, D))
+    cache.set_base_embedding(torch.zeros(64, D))
+    q = torch.from_numpy(z["query"])[None].to(DEV)
+    a, b = mm.lookup(q), cache.lookup(q)
+    assert torch.equal(a[0], b[0]) and np.array_equal(a[1].cpu().numpy()[0], z["fgram_id"])
+
+
+def test_dropin_extractor_save_load_and_fit(tmp_path):
+    sb, _ = _mods()
+    z = load_golden("fit_small.npz")
+    offs = z["corpus_offs"]
+    corpus = [z["corpus_flat"][offs[i]:offs[i + 1]].tolist() for i in range(len(offs) - 1)]
+    ex = sb.NGramExtractor(max_n=int(z["max_n"]), min_freq=int(z["min_freq"]), max_f_grams=int(z["max_f_grams"]))
+    assert ex.fit(corpus, verbose=False) is ex
+    t, l = ex.vocab_arrays()
+    assert np.array_equal(t, z["vocab_tokens"]) and np.array_equal(l, z["vocab_lens"])   # same ids as the reference fit
+    p = str(tmp_path / "ex.npy")
+    ex.save(p)
+    ex2 = sb.NGramExtractor.load(p)
+    assert ex2.f_gram_to_id == ex.f_gram_to_id and ex2.max_n == ex.max_n
+    fid, ml = ex2.lookup(torch.from_numpy(z["query"]).to(DEV))
+    assert np.array_equal(fid.cpu().numpy(), z["fgram_id"]) and np.array_equal(ml.cpu().numpy(), z["match_len"])
+
+
+def test_input_embedding_module():
+    sb, S = _mods()
+    toks, lens = S.make_vocab_numpy(800, 3, 200, seed=3)
+    ex = sb.NGramExtractor.from_arrays(toks, lens)
+    cache = sb.EmbeddingCache(ex, 128, quant="int8", out_dtype=torch.float16)
+    cache.cache_embeddings(list(range(800)), torch.from_numpy(S.make_rows_numpy(800, 128)), verbose=False)
+    wte, wpe = torch.randn(200, 128) * 0.02, torch.randn(64, 128) * 0.01
+    mod = sb.SconeInputEmbedding(cache, wte, wpe)
+    q = torch.from_numpy(S.make_stream_numpy(toks, lens, 4, 64, 200)).to(DEV)
+    emb, fid, ml = mod(q, return_match=True)
+    plain, fid2, _ = cache.lookup(q)
+    assert emb.shape == (4, 64, 128) and emb.dtype == torch.float16 and torch.equal(fid, fid2)
+    want = (plain.float() + wpe.to(DEV).half().float()[None]).half()
+    assert torch.equal(emb, want)

@@ -1,0 +1,107 @@
+"""CPU tests of the host side: C-ABI surface, drop-in host logic, synthetic generators."""
+
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden
+from oracle import py_oracle as po
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from scone_b200 import _lib, build
+    build.build()
+    L = _lib.load()
+    header = open(os.path.join(ROOT, "include", "scone_b200.h")).read()
+    declared = set(re.findall(r"\b(scone_[a-z0-9_]+)\s*\(", header))
+    declared -= {"scone_index_create_ex"}
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    for name in declared:
+        assert getattr(L, name) is not None
+    assert L.scone_version() == 100
+    assert ctypes.sizeof(_lib.TableDesc) == 40 and ctypes.sizeof(_lib.IndexInfo) == 40
+
+
+def test_table_layout_matches_oracle_packing():
+    from scone_b200 import table_layout
+    from scone_b200.utils.synthetic import pack_table_numpy
+    rows = (np.random.default_rng(0).standard_normal((4, 1024)) * 0.02).astype(np.float32)
+    for quant, want in (("fp16", (2048, 0)), ("int8", (1056, 1024)), ("int4", (544, 512))):
+        assert table_layout(quant, 1024) == want
+        t = po.OracleTable.from_fp32(rows, quant)
+        _, stride, soff = pack_table_numpy(quant, t.payload, t.scales)
+        assert (stride, soff) == want
+    assert table_layout("int4", 4096) == (2112, 2048)            # R = D/2 + 2 D/128
+    with pytest.raises(ValueError):
+        table_layout("int4", 100)
+    with pytest.raises(ValueError):
+        table_layout("fp16", 12)
+
+
+def test_invalid_arguments_fail_loudly_without_a_gpu():
+    import torch
+    import scone_b200
+    with pytest.raises(ValueError):
+        scone_b200.FGramIndex(torch.zeros((1, 2), dtype=torch.int32), torch.ones((1,), dtype=torch.uint8))   # CPU tensors
+    if not torch.cuda.is_available():
+        ex = scone_b200.NGramExtractor.from_arrays(np.array([[1, 2]], np.int32), np.array([2], np.uint8))
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            ex.get_token_f_grams([1, 2, 3])
+
+
+def test_host_fit_matches_reference_fixtures():
+    from scone_b200 import NGramExtractor
+    z = load_golden("fit_small.npz")
+    offs = z["corpus_offs"]
+    corpus = [z["corpus_flat"][offs[i]:offs[i + 1]].tolist() for i in range(len(offs) - 1)]
+    ex = NGramExtractor(int(z["max_n"]), int(z["min_freq"]), int(z["max_f_grams"])).fit(corpus, verbose=False)
+    t, l = ex.vocab_arrays()
+    assert np.array_equal(t, z["vocab_tokens"]) and np.array_equal(l, z["vocab_lens"])
+    k = load_golden("kat0.npz")
+    ex = NGramExtractor(3, 1, 100).fit([[1, 2, 3, 4, 1, 2, 3], [2, 3, 4, 5], [1, 2, 9]], verbose=False)
+    assert np.array_equal(ex.vocab_arrays()[0], k["vocab_tokens"])
+    ex = NGramExtractor(2, 2, 3).fit([[7, 8, 7, 8, 9]], verbose=False)
+    assert ex.f_gram_to_id == {(7,): 0, (8,): 1, (7, 8): 2}
+    # fuzz against the oracle's restatement of fit
+    rng = np.random.default_rng(8)
+    for _ in range(25):
+        corpus = [rng.integers(0, 12, size=int(rng.integers(0, 30))).tolist() for _ in range(int(rng.integers(1, 8)))]
+        max_n, min_freq, cap = int(rng.integers(1, 5)), int(rng.integers(1, 4)), int(rng.integers(1, 60))
+        ex = NGramExtractor(max_n, min_freq, cap).fit(corpus, verbose=False)
+        want = po.fit(corpus, max_n, min_freq, cap)
+        assert [ex.id_to_f_gram[i] for i in range(len(ex))] == want
+        assert ex.extract_all_n_grams(corpus[0]) == po.extract_all_n_grams(corpus[0], max_n)
+
+
+def test_extractor_save_load_reference_format(tmp_path):
+    from scone_b200 import NGramExtractor
+    ex = NGramExtractor(3, 1, 50).fit([[1, 2, 3, 1, 2], [4, 5]], verbose=False)
+    p = str(tmp_path / "e.npy")
+    ex.save(p)
+    raw = np.load(p, allow_pickle=True).item()
+    assert set(raw) == {"max_n", "min_freq", "max_f_grams", "f_gram_to_id"} and "1,2" in raw["f_gram_to_id"]
+    back = NGramExtractor.load(p)
+    assert back.f_gram_to_id == ex.f_gram_to_id and back.id_to_f_gram == ex.id_to_f_gram and back.f_grams == ex.f_grams
+
+
+def test_synthetic_generators():
+    from scone_b200.utils import synthetic as S
+    t, l = S.make_vocab_numpy(2000, 5, 300, seed=1)
+    keys = {tuple(t[i, :l[i]]) for i in range(2000)}
+    assert len(keys) == 2000 and l.min() >= 2 and l.max() == 5 and (t[np.arange(2000), l - 1] >= 0).all()
+    q = S.make_stream_numpy(t, l, 4, 128, 300, seed=2)
+    assert q.shape == (4, 128) and q.min() >= 0 and q.max() < 300
+    from conftest import vocab_dict
+    fid, _ = po.match_batch(vocab_dict(t, l), 5, q)
+    assert (fid >= 0).mean() > 0.5
+    import torch
+    td, ld, longest = S.make_vocab_device(5000, 4, 100, seed=0, device="cpu", return_longest=True)
+    keys = {tuple(td[i, :ld[i]].tolist()) for i in range(5000)}
+    assert len(keys) == 5000 and int(ld.min()) == 2 and int(ld.max()) == 4 and bool((ld[longest] == 4).all())
+    qd = S.make_stream_device(td, ld, 2, 64, 100, seed=1, p_plant=1.0, pick_ids=longest)
+    assert qd.shape == (2, 64) and qd.dtype == torch.int64
+    fid, _ = po.match_batch(vocab_dict(td.numpy(), ld.numpy()), 4, qd.numpy())
+    assert (fid >= 0).mean() > 0.7
