@@ -15,6 +15,8 @@
 //   * cache rows / fallback rows are read with ld.global.nc.L1::no_allocate (touched once),
 //     the output is written with st.global.cs 128-bit stores; slots use default caching so the
 //     (much smaller) index stays L2-resident.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "match.cuh"
 
@@ -52,8 +54,8 @@ __device__ __forceinline__ uint4 pack16x8(const float (&x)[8]) {
     return OUT == SCONE_OUT_BF16 ? pack_bf16x8(x) : pack_fp16x8(x);
 }
 
-template <int QUANT, int OUT, int P, int U>
-__global__ void __launch_bounds__(256, 4) embed_kernel(const EmbedParams p) {
+template <int QUANT, int OUT, int P, int U, int MINB>
+__global__ void __launch_bounds__(256, MINB) embed_kernel(const EmbedParams p) {
     constexpr int G = 32 / P;
     constexpr unsigned FULL = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
@@ -179,12 +181,31 @@ __global__ void __launch_bounds__(256, 4) embed_kernel(const EmbedParams p) {
 
 static int lanes_per_token(int max_n) { return max_n <= 1 ? 1 : max_n <= 2 ? 2 : max_n <= 4 ? 4 : 8; }
 
+// Tuning hook (tools/tune_embed.py): SCONE_EMBED_VARIANT="U:MINB" selects another instantiation of the same
+// kernel for the combinations compiled below; anything else runs the default.
+static void variant(int &u, int &minb) {
+    u = 0;
+    minb = 0;
+    if (const char *e = getenv("SCONE_EMBED_VARIANT")) sscanf(e, "%d:%d", &u, &minb);
+}
+
 template <int QUANT, int OUT, int P>
 static void launch(const EmbedParams &p, cudaStream_t stream) {
     constexpr int G = 32 / P;
     const int64_t windows = (p.T + G - 1) / G;
     const unsigned blocks = (unsigned)((windows + 7) / 8);
-    embed_kernel<QUANT, OUT, P, 4><<<blocks, 256, 0, stream>>>(p);
+    if constexpr (OUT == SCONE_OUT_BF16 && (P == 4 || P == 8)) {
+        int u, minb;
+        variant(u, minb);
+#define SCONE_V(UU, MM)                                                                  \
+    if (u == UU && minb == MM) {                                                         \
+        embed_kernel<QUANT, OUT, P, UU, MM><<<blocks, 256, 0, stream>>>(p);              \
+        return;                                                                          \
+    }
+        SCONE_V(4, 3) SCONE_V(4, 6) SCONE_V(4, 8) SCONE_V(8, 2) SCONE_V(8, 3) SCONE_V(8, 4) SCONE_V(2, 8) SCONE_V(16, 2)
+#undef SCONE_V
+    }
+    embed_kernel<QUANT, OUT, P, 4, 4><<<blocks, 256, 0, stream>>>(p);
 }
 
 template <int QUANT, int OUT>

@@ -38,6 +38,9 @@ def make_vocab_numpy(N: int, max_n: int, V: int, seed: int = 0, min_n: int = 2, 
     """
     rng = np.random.default_rng(seed)
     min_n = max(1, min(min_n, max_n))
+    capacity = sum(float(V) ** n for n in range(min_n, max_n + 1))
+    if N > 0.25 * capacity:
+        raise ValueError(f"cannot draw {N} distinct f-grams of length {min_n}..{max_n} over {V} tokens")
     seen, grams = set(), []
     while len(grams) < N:
         m = max(1024, N - len(grams))
