@@ -151,6 +151,31 @@ __device__ __forceinline__ void stg_stream_16(void *p, uint4 v) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// mbarrier (shared-memory transaction barrier) primitives, used as plain arrive/wait barriers between
+// the matcher warp and the gather warps of a CTA
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.release.cta.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
 // decode of 8 consecutive elements to fp32 (exact integer -> float, then ONE fp32 multiply)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void decode_fp16x8(uint4 raw, float (&x)[8]) {

@@ -7,14 +7,16 @@
 // scone/models/language_model.py:239-243), with Algorithm-2 (replace-or-fallback) semantics.
 //
 // Shape of the kernel (HBM-bound gather, no tensor cores):
-//   * a warp owns G = 32/P consecutive positions; phase 1 resolves their f-gram ids in registers
-//     (match.cuh), phase 2 streams their rows.
-//   * phase 2 flattens the warp's work into items (position, 256-element step): each lane owns 8
-//     consecutive elements of an item = one 16 B output vector.  U items are loaded back to back
-//     before any is converted, so a warp keeps U x 32 vector loads in flight.
-//   * cache rows / fallback rows are read with ld.global.nc.L1::no_allocate (touched once),
-//     the output is written with st.global.cs 128-bit stores; slots use default caching so the
-//     (much smaller) index stays L2-resident.
+//   * persistent CTAs (a multiple of the 148 SMs), each 1 MATCHER warp + 8 GATHER warps.
+//   * the matcher walks the CTA's tiles (a tile = the G = 32/P consecutive positions one warp can match
+//     at once, match.cuh), resolves their f-gram ids and pushes (row id, fallback token) into a small
+//     shared-memory ring guarded by mbarriers.  It runs up to kRing tiles ahead, so the dependent
+//     chain ids -> hash -> slot -> (re-probe) is off the streaming warps' critical path.
+//   * a gather warp pops one position at a time and streams its row: each lane owns 8 consecutive
+//     elements (one 16 B output vector) per 256-element step, U steps are loaded back to back before
+//     any is converted.  Cache / fallback rows are read with ld.global.nc.L1::no_allocate (touched
+//     once), the output is written with 128-bit st.global.cs; slots use default caching so the much
+//     smaller index stays L2-resident.
 #include <cstdlib>
 
 #include "common.cuh"
@@ -24,7 +26,7 @@ namespace scone {
 
 struct EmbedParams {
     IndexView ix;
-    const int32_t *fgram_in;  // not NULL: ids already resolved, skip phase 1
+    const int32_t *fgram_in;  // not NULL: ids already resolved, the matcher only forwards them
     const uint8_t *rows;
     int64_t row_stride;
     int64_t num_rows;
@@ -37,12 +39,15 @@ struct EmbedParams {
     int32_t *out_id;
     uint8_t *out_len;
     uint32_t *status;
+    int64_t num_tiles;
     int32_t D;
     int32_t scale_off;
     int32_t group_shift;  // log2(group / 8): chunk index >> group_shift = group index (INT4)
 };
 
-enum : int { kInactive = 0, kHit = 1, kMiss = 2, kZero = 3 };
+constexpr int kGatherWarps = 8;
+constexpr int kThreads = 32 * (1 + kGatherWarps);
+constexpr int kRing = 8;  // tiles the matcher may run ahead
 
 template <int OUT>
 __device__ __forceinline__ void decode16x8(uint4 raw, float (&x)[8]) {
@@ -54,132 +59,203 @@ __device__ __forceinline__ uint4 pack16x8(const float (&x)[8]) {
     return OUT == SCONE_OUT_BF16 ? pack_bf16x8(x) : pack_fp16x8(x);
 }
 
-template <int QUANT, int OUT, int P, int U, int MINB>
-__global__ void __launch_bounds__(256, MINB) embed_kernel(const EmbedParams p) {
-    constexpr int G = 32 / P;
-    constexpr unsigned FULL = 0xFFFFFFFFu;
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t base = warp * G;
-    if (base >= p.T) return;
+// ---- streaming one position -------------------------------------------------------------------------
 
-    // ---- phase 1: which row feeds each of the G positions --------------------------------------
-    const int j = lane / P;
-    const int64_t i = base + j;
-    int32_t fid = -1;
-    if (p.fgram_in) {
-        if (i < p.T) fid = __ldg(p.fgram_in + i);
-        if (fid >= p.num_rows) fid = -2;  // caller error: zero row + status
-    } else {
-        const WindowMatch m = match_window<P>(p.ix, p.ids, p.T, p.L, base, lane);
-        fid = m.fid;
-        if ((lane % P) == 0 && i < p.T) {
-            if (p.out_id) p.out_id[i] = m.fid;
-            if (p.out_len) p.out_len[i] = (uint8_t)m.len;
-        }
-    }
-    int32_t tok = -1;  // fallback row, only meaningful when fid < 0
-    if (fid == -1 && i < p.T) {
-        const int64_t t64 = __ldg(p.ids + i);
-        if (t64 >= 0 && t64 < p.V) tok = (int32_t)t64;
-    }
-
-    // ---- phase 2: stream the rows ----------------------------------------------------------------
-    const int D = p.D;
-    const int nchunks = D >> 3;
-    const int nsteps = (nchunks + 31) >> 5;
-    const int ntok = (int)((p.T - base) < (int64_t)G ? (p.T - base) : (int64_t)G);
-    const int total = ntok * nsteps;
-    const bool has_pos = p.pos != nullptr;
-    bool flagged = false;
-
-    int jj = 0, s = 0;
-    for (int w0 = 0; w0 < total; w0 += U) {
+// Hit: dequantise table row `fid` into dst.  U 256-element steps in flight per lane.
+template <int QUANT, int OUT, int U>
+__device__ __forceinline__ void stream_hit(const EmbedParams &p, int32_t fid, uint8_t *__restrict__ dst, int lane) {
+    const uint8_t *__restrict__ row = p.rows + (int64_t)fid * p.row_stride;
+    const int nchunks = p.D >> 3;
+    float rs = 1.0f;
+    if (QUANT == SCONE_QUANT_INT8) rs = __ldg(reinterpret_cast<const float *>(row + p.scale_off));
+    for (int c0 = lane; c0 < nchunks; c0 += 32 * U) {
         uint4 raw[U];
         float sc[U];
-        int kind[U];
-        int coord[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const bool act = (w0 + u) < total;       // warp-uniform
-            const int jsrc = (act ? jj : 0) * P;
-            const int32_t f = __shfl_sync(FULL, fid, jsrc);
-            const int32_t tk = __shfl_sync(FULL, tok, jsrc);
-            const int c = (s << 5) + lane;
-            kind[u] = kInactive;
-            coord[u] = (jj << 20) | c;
-            sc[u] = 1.0f;
-            raw[u] = make_uint4(0u, 0u, 0u, 0u);
-            if (act && c < nchunks) {
-                if (f >= 0) {
-                    kind[u] = kHit;
-                    const uint8_t *r = p.rows + (int64_t)f * p.row_stride;
-                    if (QUANT == SCONE_QUANT_FP16) {
-                        raw[u] = ldg_stream_16(r + c * 16);
-                    } else if (QUANT == SCONE_QUANT_INT8) {
-                        const uint2 v = ldg_stream_8(r + c * 8);
-                        raw[u].x = v.x;
-                        raw[u].y = v.y;
-                        sc[u] = __ldg(reinterpret_cast<const float *>(r + p.scale_off));
-                    } else {
-                        raw[u].x = ldg_stream_4(r + c * 4);
-                        const __half hs = __ldg(reinterpret_cast<const __half *>(r + p.scale_off) + (c >> p.group_shift));
-                        sc[u] = __half2float(hs);
-                    }
-                } else if (tk >= 0) {
-                    kind[u] = kMiss;
-                    raw[u] = ldg_stream_16(p.base + ((int64_t)tk * D + c * 8) * 2);
+            const int c = c0 + 32 * u;
+            sc[u] = rs;
+            if (c < nchunks) {
+                if (QUANT == SCONE_QUANT_FP16) {
+                    raw[u] = ldg_stream_16(row + c * 16);
+                } else if (QUANT == SCONE_QUANT_INT8) {
+                    const uint2 v = ldg_stream_8(row + c * 8);
+                    raw[u].x = v.x;
+                    raw[u].y = v.y;
                 } else {
-                    kind[u] = kZero;
+                    raw[u].x = ldg_stream_4(row + c * 4);
+                    sc[u] = __half2float(__ldg(reinterpret_cast<const __half *>(row + p.scale_off) + (c >> p.group_shift)));
                 }
-            }
-            if (act && ++s == nsteps) {
-                s = 0;
-                ++jj;
             }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            if (kind[u] == kInactive) continue;
-            const int tj = coord[u] >> 20, c = coord[u] & 0xFFFFF;
-            const int64_t t = base + tj;
-            uint4 o;
-            if (kind[u] == kMiss && !has_pos) {
-                o = raw[u];  // fallback rows are already in the output type
-            } else if (kind[u] == kZero && !has_pos) {
-                o = make_uint4(0u, 0u, 0u, 0u);
-                flagged = true;
-            } else {
-                float x[8];
-                if (kind[u] == kHit) {
+            const int c = c0 + 32 * u;
+            if (c < nchunks) {
+                uint4 o;
+                if (QUANT == SCONE_QUANT_FP16 && OUT == SCONE_OUT_FP16) {
+                    o = raw[u];
+                } else {
+                    float x[8];
                     if (QUANT == SCONE_QUANT_FP16) decode_fp16x8(raw[u], x);
                     else if (QUANT == SCONE_QUANT_INT8) decode_int8x8(make_uint2(raw[u].x, raw[u].y), sc[u], x);
                     else decode_int4x8(raw[u].x, sc[u], x);
-                } else if (kind[u] == kMiss) {
-                    decode16x8<OUT>(raw[u], x);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) x[k] = 0.0f;
-                    flagged = true;
+                    o = pack16x8<OUT>(x);
                 }
-                if (has_pos) {
-                    const int64_t pr = pos_in_row(t, p.L, p.T);
-                    const uint4 pv = __ldg(reinterpret_cast<const uint4 *>(p.pos + (pr * D + c * 8) * 2));
-                    float y[8];
-                    decode16x8<OUT>(pv, y);
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) x[k] = __fadd_rn(x[k], y[k]);
-                }
-                if (QUANT == SCONE_QUANT_FP16 && OUT == SCONE_OUT_FP16 && kind[u] == kHit && !has_pos) o = raw[u];
-                else o = pack16x8<OUT>(x);
+                stg_stream_16(dst + c * 16, o);
             }
-            stg_stream_16(p.out + (t * D + c * 8) * 2, o);
         }
     }
-    if (flagged && p.status) atomicOr(p.status, SCONE_STATUS_TOKEN_OOR);
+}
+
+// Miss: the fallback row is already in the output type -> 16 B copy.
+template <int U>
+__device__ __forceinline__ void stream_miss(const EmbedParams &p, int32_t tok, uint8_t *__restrict__ dst, int lane) {
+    const uint8_t *__restrict__ row = p.base + (int64_t)tok * p.D * 2;
+    const int nchunks = p.D >> 3;
+    for (int c0 = lane; c0 < nchunks; c0 += 32 * U) {
+        uint4 raw[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int c = c0 + 32 * u;
+            if (c < nchunks) raw[u] = ldg_stream_16(row + c * 16);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int c = c0 + 32 * u;
+            if (c < nchunks) stg_stream_16(dst + c * 16, raw[u]);
+        }
+    }
+}
+
+// Everything else (position add, out-of-range token): correctness path, not tuned.
+template <int QUANT, int OUT>
+__device__ __noinline__ void stream_general(const EmbedParams &p, int32_t fid, int32_t tok, int64_t t, uint8_t *__restrict__ dst,
+                                            int lane) {
+    const int nchunks = p.D >> 3;
+    const uint8_t *row = fid >= 0 ? p.rows + (int64_t)fid * p.row_stride : nullptr;
+    const uint8_t *brow = (fid < 0 && tok >= 0) ? p.base + (int64_t)tok * p.D * 2 : nullptr;
+    const uint8_t *prow = p.pos ? p.pos + pos_in_row(t, p.L, p.T) * p.D * 2 : nullptr;
+    for (int c = lane; c < nchunks; c += 32) {
+        float x[8];
+        if (row) {
+            if (QUANT == SCONE_QUANT_FP16) {
+                decode_fp16x8(ldg_stream_16(row + c * 16), x);
+            } else if (QUANT == SCONE_QUANT_INT8) {
+                decode_int8x8(ldg_stream_8(row + c * 8), __ldg(reinterpret_cast<const float *>(row + p.scale_off)), x);
+            } else {
+                const __half hs = __ldg(reinterpret_cast<const __half *>(row + p.scale_off) + (c >> p.group_shift));
+                decode_int4x8(ldg_stream_4(row + c * 4), __half2float(hs), x);
+            }
+        } else if (brow) {
+            decode16x8<OUT>(ldg_stream_16(brow + c * 16), x);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) x[k] = 0.0f;
+        }
+        if (prow) {
+            float y[8];
+            decode16x8<OUT>(__ldg(reinterpret_cast<const uint4 *>(prow + c * 16)), y);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) x[k] = __fadd_rn(x[k], y[k]);
+        }
+        stg_stream_16(dst + c * 16, pack16x8<OUT>(x));
+    }
+}
+
+// ---- the kernel --------------------------------------------------------------------------------------
+
+template <int QUANT, int OUT, int P, int U, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) embed_kernel(const EmbedParams p) {
+    constexpr int G = 32 / P;
+    __shared__ __align__(8) uint64_t full_bar[kRing];
+    __shared__ __align__(8) uint64_t empty_bar[kRing];
+    __shared__ int2 ring[kRing][G];  // (row id or <0, fallback token or -1)
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int q = 0; q < kRing; ++q) {
+            mbar_init(&full_bar[q], 1);
+            mbar_init(&empty_bar[q], G);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == 0) {
+        // ===== matcher: resolve tiles, run ahead of the gather warps =====
+        const int j = lane / P;
+        int it = 0;
+        for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            const int q = it % kRing;
+            const int64_t base = tile * G;
+            const int64_t i = base + j;
+            int32_t fid = -1;
+            if (p.fgram_in) {
+                if (i < p.T) fid = __ldg(p.fgram_in + i);
+                if (fid >= p.num_rows) fid = -2;  // caller error: zero row + status
+            } else {
+                const WindowMatch m = match_window<P>(p.ix, p.ids, p.T, p.L, base, lane);
+                fid = m.fid;
+                if ((lane % P) == 0 && i < p.T) {
+                    if (p.out_id) p.out_id[i] = m.fid;
+                    if (p.out_len) p.out_len[i] = (uint8_t)m.len;
+                }
+            }
+            int32_t tok = -1;
+            if (fid == -1 && i < p.T) {
+                const int64_t t64 = __ldg(p.ids + i);
+                if (t64 >= 0 && t64 < p.V) tok = (int32_t)t64;
+            }
+            mbar_wait(&empty_bar[q], ((it / kRing) & 1) ^ 1);
+            if ((lane % P) == 0) ring[q][j] = make_int2(fid, tok);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full_bar[q]);
+        }
+    } else {
+        // ===== gather warps: pop positions round-robin, stream their rows =====
+        bool flagged = false;
+        const bool general = p.pos != nullptr;
+        for (int64_t s = warp - 1;; s += kGatherWarps) {
+            const int64_t itl = s / G;
+            const int j = (int)(s - itl * G);
+            const int64_t tile = blockIdx.x + itl * gridDim.x;
+            if (tile >= p.num_tiles) break;
+            const int q = (int)(itl % kRing);
+            mbar_wait(&full_bar[q], (uint32_t)((itl / kRing) & 1));
+            const int2 e = ring[q][j];
+            const int64_t t = tile * G + j;
+            if (t < p.T) {
+                uint8_t *dst = p.out + t * p.D * 2;
+                if (general || (e.x < 0 && e.y < 0)) {
+                    stream_general<QUANT, OUT>(p, e.x, e.y, t, dst, lane);
+                    flagged |= (e.x < 0 && e.y < 0);
+                } else if (e.x >= 0) {
+                    stream_hit<QUANT, OUT, U>(p, e.x, dst, lane);
+                } else {
+                    stream_miss<U>(p, e.y, dst, lane);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[q]);
+        }
+        if (flagged && p.status && lane == 0) atomicOr(p.status, SCONE_STATUS_TOKEN_OOR);
+    }
 }
 
 static int lanes_per_token(int max_n) { return max_n <= 1 ? 1 : max_n <= 2 ? 2 : max_n <= 4 ? 4 : 8; }
+
+static int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = kNumSMsB200;
+    }
+    return n;
+}
 
 // Tuning hook (tools/tune_embed.py): SCONE_EMBED_VARIANT="U:MINB" selects another instantiation of the same
 // kernel for the combinations compiled below; anything else runs the default.
@@ -189,27 +265,33 @@ static void variant(int &u, int &minb) {
     if (const char *e = getenv("SCONE_EMBED_VARIANT")) sscanf(e, "%d:%d", &u, &minb);
 }
 
-template <int QUANT, int OUT, int P>
-static void launch(const EmbedParams &p, cudaStream_t stream) {
+template <int QUANT, int OUT, int P, int U, int MINB>
+static void launch_one(EmbedParams &p, cudaStream_t stream) {
     constexpr int G = 32 / P;
-    const int64_t windows = (p.T + G - 1) / G;
-    const unsigned blocks = (unsigned)((windows + 7) / 8);
+    p.num_tiles = (p.T + G - 1) / G;
+    const int64_t resident = (int64_t)num_sms() * MINB;
+    const unsigned blocks = (unsigned)(p.num_tiles < resident ? p.num_tiles : resident);
+    embed_kernel<QUANT, OUT, P, U, MINB><<<blocks, kThreads, 0, stream>>>(p);
+}
+
+template <int QUANT, int OUT, int P>
+static void launch(EmbedParams &p, cudaStream_t stream) {
     if constexpr (OUT == SCONE_OUT_BF16 && (P == 4 || P == 8)) {
         int u, minb;
         variant(u, minb);
-#define SCONE_V(UU, MM)                                                                  \
-    if (u == UU && minb == MM) {                                                         \
-        embed_kernel<QUANT, OUT, P, UU, MM><<<blocks, 256, 0, stream>>>(p);              \
-        return;                                                                          \
+#define SCONE_V(UU, MM)                                        \
+    if (u == UU && minb == MM) {                               \
+        launch_one<QUANT, OUT, P, UU, MM>(p, stream);          \
+        return;                                                \
     }
-        SCONE_V(4, 3) SCONE_V(4, 6) SCONE_V(4, 8) SCONE_V(8, 2) SCONE_V(8, 3) SCONE_V(8, 4) SCONE_V(2, 8) SCONE_V(16, 2)
+        SCONE_V(4, 3) SCONE_V(4, 5) SCONE_V(4, 6) SCONE_V(8, 3) SCONE_V(8, 4) SCONE_V(2, 6) SCONE_V(2, 4)
 #undef SCONE_V
     }
-    embed_kernel<QUANT, OUT, P, 4, 4><<<blocks, 256, 0, stream>>>(p);
+    launch_one<QUANT, OUT, P, 4, 4>(p, stream);
 }
 
 template <int QUANT, int OUT>
-static void launch_p(int P, const EmbedParams &p, cudaStream_t stream) {
+static void launch_p(int P, EmbedParams &p, cudaStream_t stream) {
     switch (P) {
         case 1: launch<QUANT, OUT, 1>(p, stream); break;
         case 2: launch<QUANT, OUT, 2>(p, stream); break;
@@ -218,7 +300,7 @@ static void launch_p(int P, const EmbedParams &p, cudaStream_t stream) {
     }
 }
 
-static int dispatch(int P, const EmbedParams &p, int quant, int out_dtype, cudaStream_t stream) {
+static int dispatch(int P, EmbedParams &p, int quant, int out_dtype, cudaStream_t stream) {
     if (out_dtype == SCONE_OUT_BF16) {
         if (quant == SCONE_QUANT_FP16) launch_p<SCONE_QUANT_FP16, SCONE_OUT_BF16>(P, p, stream);
         else if (quant == SCONE_QUANT_INT8) launch_p<SCONE_QUANT_INT8, SCONE_OUT_BF16>(P, p, stream);
@@ -269,6 +351,8 @@ int scone_embed_forward(const scone_index_t *index, const scone_table_desc_t *ta
     SCONE_REQUIRE(T < (1ll << 40), "scone_embed_forward: batch too large");
     SCONE_REQUIRE(d_ids && d_out, "scone_embed_forward: NULL ids or out");
     SCONE_REQUIRE(d_base_emb && base_rows > 0, "scone_embed_forward: base embedding table required (fallback rows)");
+    SCONE_REQUIRE((((uintptr_t)d_base_emb | (uintptr_t)d_out | (uintptr_t)d_pos_emb) & 15) == 0,
+                  "scone_embed_forward: base_emb, pos_emb and out must be 16-byte aligned");
     const scone_index_impl *ix = reinterpret_cast<const scone_index_impl *>(index);
     SCONE_REQUIRE(ix->n <= table->num_rows, "scone_embed_forward: index has %lld f-grams but the table only %lld rows",
                   (long long)ix->n, (long long)table->num_rows);
@@ -301,6 +385,8 @@ int scone_embed_gather(const scone_table_desc_t *table, const void *d_base_emb, 
     SCONE_REQUIRE(d_ids && d_out && d_fgram_id, "scone_embed_gather: NULL buffer");
     SCONE_REQUIRE(d_base_emb && base_rows > 0, "scone_embed_gather: base embedding table required (fallback rows)");
     SCONE_REQUIRE(!d_pos_emb || L > 0, "scone_embed_gather: L required with pos_emb");
+    SCONE_REQUIRE((((uintptr_t)d_base_emb | (uintptr_t)d_out | (uintptr_t)d_pos_emb) & 15) == 0,
+                  "scone_embed_gather: base_emb, pos_emb and out must be 16-byte aligned");
     EmbedParams p{};
     int rc = fill_table(p, table, "scone_embed_gather");
     if (rc != SCONE_OK) return rc;
