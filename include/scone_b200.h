@@ -16,7 +16,7 @@
  *   - all work is enqueued asynchronously on `stream` (a cudaStream_t passed
  *     as void*); buffers must stay alive until the stream is synchronised.
  *     The only calls that synchronise are scone_index_create (one read-back of
- *     the build audit) and scone_status_read.
+ *     the build audit).
  *   - return value: 0 = OK, negative = error (SCONE_E_*); the message is
  *     available from scone_last_error() on the calling thread.
  *   - there is NO CPU fallback: without a CUDA device every compute entry
@@ -94,7 +94,8 @@ const char *scone_last_error(void);
  * The open-addressing table (32-byte slots, key stored inline, home slot from a
  * rolling 64-bit hash) is built by kernels on `stream`; the call then reads back a
  * build audit and fails with SCONE_E_VOCAB if two rows hold the same f-gram, a length
- * is outside [1, max_n] or a token is negative.  load_factor in (0, 0.9]; <= 0 -> 0.5. */
+ * is outside [1, max_n] or a token is negative.  load_factor in (0, 0.9]; <= 0 -> 0.25 (128 B of index per
+ * f-gram: short probe chains matter more than index size). */
 int scone_index_create(const int32_t *d_tokens, const uint8_t *d_lens, int64_t n, int32_t max_n,
                        double load_factor, void *stream, scone_index_t **out);
 int scone_index_destroy(scone_index_t *index);

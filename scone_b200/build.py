@@ -46,7 +46,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + \
+    tune = ["-DSCONE_TUNE"] if os.environ.get("SCONE_TUNE") else []      # extra kernel variants for tools/tune_embed.py
+    cmd = [nvcc_path()] + NVCC_FLAGS + tune + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + \
           [os.path.join(CSRC, s) for s in SOURCES]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:

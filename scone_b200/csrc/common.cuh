@@ -103,7 +103,8 @@ __device__ __forceinline__ uint64_t home_slot(uint64_t h, uint64_t cap) { return
 
 // 256-bit slot load (LDG.E.256); slots are read-only while any lookup runs.
 __device__ __forceinline__ void load_slot(const Slot *p, int32_t (&w)[8]) {
-    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+    // evict-last in L1 and L2: the index is re-read by every batch, the streamed rows are not
+    asm volatile("ld.global.nc.L1::evict_last.L2::evict_last.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
                  : "l"(p));
 }
@@ -127,6 +128,36 @@ __device__ __forceinline__ int32_t probe(const IndexView &ix, uint64_t h, const 
 // ---------------------------------------------------------------------------------------------
 // vector memory helpers
 // ---------------------------------------------------------------------------------------------
+// L2 evict-first policy for everything that is touched once (cache rows, fallback rows, the output):
+// keeps the 126 MB L2 for the index slots.
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint4 ldg_stream_16(const void *p, uint64_t pol) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.b32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ uint2 ldg_stream_8(const void *p, uint64_t pol) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.b32 {%0,%1}, [%2], %3;" : "=r"(r.x), "=r"(r.y) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ uint32_t ldg_stream_4(const void *p, uint64_t pol) {
+    uint32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ void stg_stream_16(void *p, uint4 v, uint64_t pol) {
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.b32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w),
+                 "l"(pol)
+                 : "memory");
+}
+
 // streaming read of data touched once (cache rows, fallback rows): no L1 allocation
 __device__ __forceinline__ uint4 ldg_stream_16(const void *p) {
     uint4 r;
@@ -173,6 +204,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "}" ::"r"(smem_u32(bar)),
         "r"(parity)
         : "memory");
+}
+
+// one arrival that also announces `tx_bytes` of asynchronous (bulk-copy) traffic for this phase
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t tx_bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.release.cta.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+                 "r"(tx_bytes)
+                 : "memory");
+}
+// TMA 1-D bulk copy global -> shared (UBLKCP); completion is signalled on `bar` as `bytes` of tx.
+// dst, src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+                 : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------

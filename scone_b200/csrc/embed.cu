@@ -45,9 +45,7 @@ struct EmbedParams {
     int32_t group_shift;  // log2(group / 8): chunk index >> group_shift = group index (INT4)
 };
 
-constexpr int kGatherWarps = 8;
-constexpr int kThreads = 32 * (1 + kGatherWarps);
-constexpr int kRing = 8;  // tiles the matcher may run ahead
+constexpr int kRing = 16;  // tiles the matchers may run ahead of the gather warps
 
 template <int OUT>
 __device__ __forceinline__ void decode16x8(uint4 raw, float (&x)[8]) {
@@ -63,7 +61,7 @@ __device__ __forceinline__ uint4 pack16x8(const float (&x)[8]) {
 
 // Hit: dequantise table row `fid` into dst.  U 256-element steps in flight per lane.
 template <int QUANT, int OUT, int U>
-__device__ __forceinline__ void stream_hit(const EmbedParams &p, int32_t fid, uint8_t *__restrict__ dst, int lane) {
+__device__ __forceinline__ void stream_hit(const EmbedParams &p, int32_t fid, uint8_t *__restrict__ dst, int lane, uint64_t pol) {
     const uint8_t *__restrict__ row = p.rows + (int64_t)fid * p.row_stride;
     const int nchunks = p.D >> 3;
     float rs = 1.0f;
@@ -77,13 +75,13 @@ __device__ __forceinline__ void stream_hit(const EmbedParams &p, int32_t fid, ui
             sc[u] = rs;
             if (c < nchunks) {
                 if (QUANT == SCONE_QUANT_FP16) {
-                    raw[u] = ldg_stream_16(row + c * 16);
+                    raw[u] = ldg_stream_16(row + c * 16, pol);
                 } else if (QUANT == SCONE_QUANT_INT8) {
-                    const uint2 v = ldg_stream_8(row + c * 8);
+                    const uint2 v = ldg_stream_8(row + c * 8, pol);
                     raw[u].x = v.x;
                     raw[u].y = v.y;
                 } else {
-                    raw[u].x = ldg_stream_4(row + c * 4);
+                    raw[u].x = ldg_stream_4(row + c * 4, pol);
                     sc[u] = __half2float(__ldg(reinterpret_cast<const __half *>(row + p.scale_off) + (c >> p.group_shift)));
                 }
             }
@@ -102,7 +100,7 @@ __device__ __forceinline__ void stream_hit(const EmbedParams &p, int32_t fid, ui
                     else decode_int4x8(raw[u].x, sc[u], x);
                     o = pack16x8<OUT>(x);
                 }
-                stg_stream_16(dst + c * 16, o);
+                stg_stream_16(dst + c * 16, o, pol);
             }
         }
     }
@@ -110,7 +108,7 @@ __device__ __forceinline__ void stream_hit(const EmbedParams &p, int32_t fid, ui
 
 // Miss: the fallback row is already in the output type -> 16 B copy.
 template <int U>
-__device__ __forceinline__ void stream_miss(const EmbedParams &p, int32_t tok, uint8_t *__restrict__ dst, int lane) {
+__device__ __forceinline__ void stream_miss(const EmbedParams &p, int32_t tok, uint8_t *__restrict__ dst, int lane, uint64_t pol) {
     const uint8_t *__restrict__ row = p.base + (int64_t)tok * p.D * 2;
     const int nchunks = p.D >> 3;
     for (int c0 = lane; c0 < nchunks; c0 += 32 * U) {
@@ -118,12 +116,12 @@ __device__ __forceinline__ void stream_miss(const EmbedParams &p, int32_t tok, u
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int c = c0 + 32 * u;
-            if (c < nchunks) raw[u] = ldg_stream_16(row + c * 16);
+            if (c < nchunks) raw[u] = ldg_stream_16(row + c * 16, pol);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int c = c0 + 32 * u;
-            if (c < nchunks) stg_stream_16(dst + c * 16, raw[u]);
+            if (c < nchunks) stg_stream_16(dst + c * 16, raw[u], pol);
         }
     }
 }
@@ -165,9 +163,11 @@ __device__ __noinline__ void stream_general(const EmbedParams &p, int32_t fid, i
 
 // ---- the kernel --------------------------------------------------------------------------------------
 
-template <int QUANT, int OUT, int P, int U, int MINB>
-__global__ void __launch_bounds__(kThreads, MINB) embed_kernel(const EmbedParams p) {
+template <int QUANT, int OUT, int P, int U, int NM, int NG, int MINB>
+__global__ void __launch_bounds__(32 * (NM + NG), MINB) embed_kernel(const EmbedParams p) {
     constexpr int G = 32 / P;
+    static_assert(kRing >= NM, "ring must hold the tiles all matchers have in flight");
+    constexpr int R = kRing / NM * NM;  // slot ownership: a ring slot is only ever filled by one matcher
     __shared__ __align__(8) uint64_t full_bar[kRing];
     __shared__ __align__(8) uint64_t empty_bar[kRing];
     __shared__ int2 ring[kRing][G];  // (row id or <0, fallback token or -1)
@@ -178,64 +178,262 @@ __global__ void __launch_bounds__(kThreads, MINB) embed_kernel(const EmbedParams
 #pragma unroll
         for (int q = 0; q < kRing; ++q) {
             mbar_init(&full_bar[q], 1);
-            mbar_init(&empty_bar[q], G);
+            mbar_init(&empty_bar[q], NG);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    if (warp == 0) {
-        // ===== matcher: resolve tiles, run ahead of the gather warps =====
+    if (warp < NM) {
+        // ===== matcher warps: resolve the CTA's tiles round-robin, running ahead of the gather warps =====
         const int j = lane / P;
-        int it = 0;
-        for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-            const int q = it % kRing;
+        int64_t it = warp;
+        int64_t tile = blockIdx.x + it * gridDim.x;
+        int32_t wtok = -1;
+        if (!p.fgram_in && tile < p.num_tiles) wtok = load_window_token<P>(p.ids, p.T, tile * G, lane);
+        for (; tile < p.num_tiles; it += NM, tile += (int64_t)NM * gridDim.x) {
+            const int q = (int)(it % R);
             const int64_t base = tile * G;
             const int64_t i = base + j;
-            int32_t fid = -1;
+            // the ids of this warp's NEXT tile are requested before the dependent probe chain of this one
+            const int64_t ntile = tile + (int64_t)NM * gridDim.x;
+            int32_t ntok = -1;
+            int32_t fid = -1, tok = -1;
             if (p.fgram_in) {
-                if (i < p.T) fid = __ldg(p.fgram_in + i);
-                if (fid >= p.num_rows) fid = -2;  // caller error: zero row + status
+                if (i < p.T) {
+                    fid = __ldg(p.fgram_in + i);
+                    if (fid >= p.num_rows) fid = -2;  // caller error: zero row + status
+                    if (fid == -1) {
+                        const int64_t t64 = __ldg(p.ids + i);
+                        if (t64 >= 0 && t64 < p.V) tok = (int32_t)t64;
+                    }
+                }
             } else {
-                const WindowMatch m = match_window<P>(p.ix, p.ids, p.T, p.L, base, lane);
+                if (ntile < p.num_tiles) ntok = load_window_token<P>(p.ids, p.T, ntile * G, lane);
+                const WindowMatch m = match_window<P>(p.ix, wtok, p.T, p.L, base, lane);
                 fid = m.fid;
+                tok = own_token<P>(wtok, lane);
+                if ((int64_t)tok >= p.V) tok = -1;
                 if ((lane % P) == 0 && i < p.T) {
                     if (p.out_id) p.out_id[i] = m.fid;
                     if (p.out_len) p.out_len[i] = (uint8_t)m.len;
                 }
+                wtok = ntok;
             }
-            int32_t tok = -1;
-            if (fid == -1 && i < p.T) {
-                const int64_t t64 = __ldg(p.ids + i);
-                if (t64 >= 0 && t64 < p.V) tok = (int32_t)t64;
-            }
-            mbar_wait(&empty_bar[q], ((it / kRing) & 1) ^ 1);
-            if ((lane % P) == 0) ring[q][j] = make_int2(fid, tok);
+            mbar_wait(&empty_bar[q], (uint32_t)(((it / R) & 1) ^ 1));
+            if ((lane % P) == 0) ring[q][j] = make_int2(fid, fid == -1 ? tok : -1);
             __syncwarp();
             if (lane == 0) mbar_arrive(&full_bar[q]);
         }
     } else {
-        // ===== gather warps: pop positions round-robin, stream their rows =====
+        // ===== gather warps: walk the CTA's tiles in order, stream the positions they own =====
+        // Position s = itl * G + j of the CTA's sequence belongs to gather warp s % NG.  EVERY gather warp waits
+        // for and releases EVERY tile (even one in which it owns nothing): with parity-only mbarriers this is
+        // what guarantees that no waiter is ever more than one phase away from the barrier's current phase.
         bool flagged = false;
         const bool general = p.pos != nullptr;
-        for (int64_t s = warp - 1;; s += kGatherWarps) {
-            const int64_t itl = s / G;
-            const int j = (int)(s - itl * G);
-            const int64_t tile = blockIdx.x + itl * gridDim.x;
-            if (tile >= p.num_tiles) break;
-            const int q = (int)(itl % kRing);
-            mbar_wait(&full_bar[q], (uint32_t)((itl / kRing) & 1));
-            const int2 e = ring[q][j];
-            const int64_t t = tile * G + j;
-            if (t < p.T) {
-                uint8_t *dst = p.out + t * p.D * 2;
-                if (general || (e.x < 0 && e.y < 0)) {
-                    stream_general<QUANT, OUT>(p, e.x, e.y, t, dst, lane);
-                    flagged |= (e.x < 0 && e.y < 0);
-                } else if (e.x >= 0) {
-                    stream_hit<QUANT, OUT, U>(p, e.x, dst, lane);
+        const uint64_t pol = policy_evict_first();
+        const int w = warp - NM;
+        int64_t itl = 0;
+        for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++itl) {
+            const int q = (int)(itl % R);
+            mbar_wait(&full_bar[q], (uint32_t)((itl / R) & 1));
+            const int first = (int)(((int64_t)w - (itl * G) % NG + NG) % NG);
+            for (int j = first; j < G; j += NG) {
+                const int2 e = ring[q][j];
+                const int64_t t = tile * G + j;
+                if (t < p.T) {
+                    uint8_t *dst = p.out + t * p.D * 2;
+                    if (general || (e.x < 0 && e.y < 0)) {
+                        stream_general<QUANT, OUT>(p, e.x, e.y, t, dst, lane);
+                        flagged |= (e.x < 0 && e.y < 0);
+                    } else if (e.x >= 0) {
+                        stream_hit<QUANT, OUT, U>(p, e.x, dst, lane, pol);
+                    } else {
+                        stream_miss<U>(p, e.y, dst, lane, pol);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[q]);
+        }
+        if (flagged && p.status && lane == 0) atomicOr(p.status, SCONE_STATUS_TOKEN_OOR);
+    }
+}
+
+// ---- variant B: rows land in shared memory through TMA bulk copies ---------------------------------------
+//
+// Same roles, but the matcher that resolved a tile also issues one cp.async.bulk (global -> shared, 1-D) per
+// position into the tile's ring slot; the slot's mbarrier completes when the matcher has arrived AND all row
+// bytes have landed.  Loads in flight are then bounded by shared memory (tens of KB per CTA) instead of by the
+// gather warps' registers, and the gather warps only touch shared memory and issue the output stores.
+
+struct BulkLayout {
+    int ring;        // ring slots (tiles in flight per CTA)
+    int slot_bytes;  // bytes reserved per position (>= max(row_stride, 2 D), multiple of 128)
+    int smem_bytes;  // dynamic shared memory per CTA
+};
+
+template <int QUANT, int OUT>
+__device__ __forceinline__ void stream_from_smem(const EmbedParams &p, const uint8_t *srow, int32_t fid, int32_t tok, int64_t t,
+                                                 uint8_t *__restrict__ dst, int lane, uint64_t pol) {
+    const int nchunks = p.D >> 3;
+    const uint8_t *prow = p.pos ? p.pos + pos_in_row(t, p.L, p.T) * p.D * 2 : nullptr;
+    if (fid >= 0 && !prow) {
+        float rs = 1.0f;
+        if (QUANT == SCONE_QUANT_INT8) rs = *reinterpret_cast<const float *>(srow + p.scale_off);
+#pragma unroll 4
+        for (int c = lane; c < nchunks; c += 32) {
+            uint4 o;
+            if (QUANT == SCONE_QUANT_FP16 && OUT == SCONE_OUT_FP16) {
+                o = *reinterpret_cast<const uint4 *>(srow + c * 16);
+            } else {
+                float x[8];
+                if (QUANT == SCONE_QUANT_FP16) {
+                    decode_fp16x8(*reinterpret_cast<const uint4 *>(srow + c * 16), x);
+                } else if (QUANT == SCONE_QUANT_INT8) {
+                    decode_int8x8(*reinterpret_cast<const uint2 *>(srow + c * 8), rs, x);
                 } else {
-                    stream_miss<U>(p, e.y, dst, lane);
+                    const float sc = __half2float(*(reinterpret_cast<const __half *>(srow + p.scale_off) + (c >> p.group_shift)));
+                    decode_int4x8(*reinterpret_cast<const uint32_t *>(srow + c * 4), sc, x);
+                }
+                o = pack16x8<OUT>(x);
+            }
+            stg_stream_16(dst + c * 16, o, pol);
+        }
+    } else if (fid < 0 && tok >= 0 && !prow) {
+#pragma unroll 4
+        for (int c = lane; c < nchunks; c += 32) stg_stream_16(dst + c * 16, *reinterpret_cast<const uint4 *>(srow + c * 16), pol);
+    } else {
+        for (int c = lane; c < nchunks; c += 32) {
+            float x[8];
+            if (fid >= 0) {
+                if (QUANT == SCONE_QUANT_FP16) {
+                    decode_fp16x8(*reinterpret_cast<const uint4 *>(srow + c * 16), x);
+                } else if (QUANT == SCONE_QUANT_INT8) {
+                    decode_int8x8(*reinterpret_cast<const uint2 *>(srow + c * 8), *reinterpret_cast<const float *>(srow + p.scale_off), x);
+                } else {
+                    const float sc = __half2float(*(reinterpret_cast<const __half *>(srow + p.scale_off) + (c >> p.group_shift)));
+                    decode_int4x8(*reinterpret_cast<const uint32_t *>(srow + c * 4), sc, x);
+                }
+            } else if (tok >= 0) {
+                decode16x8<OUT>(*reinterpret_cast<const uint4 *>(srow + c * 16), x);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) x[k] = 0.0f;
+            }
+            if (prow) {
+                float y[8];
+                decode16x8<OUT>(__ldg(reinterpret_cast<const uint4 *>(prow + c * 16)), y);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) x[k] = __fadd_rn(x[k], y[k]);
+            }
+            stg_stream_16(dst + c * 16, pack16x8<OUT>(x), pol);
+        }
+    }
+}
+
+constexpr int kMaxRing = 16;
+// bytes of barriers + ring metadata in front of the row slots
+__host__ __device__ constexpr int bulk_header_bytes(int G) { return (2 * kMaxRing * 8 + kMaxRing * G * 8 + 127) / 128 * 128; }
+
+template <int QUANT, int OUT, int P, int NM, int NG, int MINB>
+__global__ void __launch_bounds__(32 * (NM + NG), MINB) embed_bulk_kernel(const EmbedParams p, const BulkLayout lay) {
+    constexpr int G = 32 / P;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem);
+    uint64_t *empty_bar = full_bar + kMaxRing;
+    int2 *ring = reinterpret_cast<int2 *>(empty_bar + kMaxRing);  // [ring][G]
+    uint8_t *rows_smem = smem + bulk_header_bytes(G);
+    const int R = lay.ring;
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        for (int q = 0; q < R; ++q) {
+            mbar_init(&full_bar[q], 1);
+            mbar_init(&empty_bar[q], NG);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp < NM) {
+        const int j = lane / P;
+        const uint64_t pol = policy_evict_first();
+        int64_t it = warp;
+        int64_t tile = blockIdx.x + it * gridDim.x;
+        int32_t wtok = -1;
+        if (!p.fgram_in && tile < p.num_tiles) wtok = load_window_token<P>(p.ids, p.T, tile * G, lane);
+        for (; tile < p.num_tiles; it += NM, tile += (int64_t)NM * gridDim.x) {
+            const int q = (int)(it % R);
+            const int64_t base = tile * G;
+            const int64_t i = base + j;
+            const int64_t ntile = tile + (int64_t)NM * gridDim.x;
+            int32_t ntok = -1;
+            int32_t fid = -1, tok = -1;
+            if (p.fgram_in) {
+                if (i < p.T) {
+                    fid = __ldg(p.fgram_in + i);
+                    if (fid >= p.num_rows) fid = -2;
+                    if (fid == -1) {
+                        const int64_t t64 = __ldg(p.ids + i);
+                        if (t64 >= 0 && t64 < p.V) tok = (int32_t)t64;
+                    }
+                }
+            } else {
+                if (ntile < p.num_tiles) ntok = load_window_token<P>(p.ids, p.T, ntile * G, lane);
+                const WindowMatch m = match_window<P>(p.ix, wtok, p.T, p.L, base, lane);
+                fid = m.fid;
+                tok = own_token<P>(wtok, lane);
+                if ((int64_t)tok >= p.V) tok = -1;
+                if ((lane % P) == 0 && i < p.T) {
+                    if (p.out_id) p.out_id[i] = m.fid;
+                    if (p.out_len) p.out_len[i] = (uint8_t)m.len;
+                }
+                wtok = ntok;
+            }
+            if (fid != -1) tok = -1;
+            // source of this position's bytes
+            const bool owner = (lane % P) == 0 && i < p.T;
+            const uint8_t *src = nullptr;
+            uint32_t bytes = 0;
+            if (owner) {
+                if (fid >= 0) {
+                    src = p.rows + (int64_t)fid * p.row_stride;
+                    bytes = (uint32_t)p.row_stride;
+                } else if (tok >= 0) {
+                    src = p.base + (int64_t)tok * p.D * 2;
+                    bytes = (uint32_t)p.D * 2u;
+                }
+            }
+            uint32_t total = bytes;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xFFFFFFFFu, total, o);
+            mbar_wait(&empty_bar[q], (uint32_t)(((it / R) & 1) ^ 1));
+            if ((lane % P) == 0) ring[q * G + j] = make_int2(fid, tok);
+            __syncwarp();
+            if (lane == 0) mbar_arrive_expect_tx(&full_bar[q], total);
+            __syncwarp();
+            if (bytes) bulk_g2s(rows_smem + (size_t)(q * G + j) * lay.slot_bytes, src, bytes, &full_bar[q], pol);
+        }
+    } else {
+        // every gather warp waits for and releases every tile, in order (see embed_kernel)
+        bool flagged = false;
+        const uint64_t pol = policy_evict_first();
+        const int w = warp - NM;
+        int64_t itl = 0;
+        for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++itl) {
+            const int q = (int)(itl % R);
+            mbar_wait(&full_bar[q], (uint32_t)((itl / R) & 1));
+            const int first = (int)(((int64_t)w - (itl * G) % NG + NG) % NG);
+            for (int j = first; j < G; j += NG) {
+                const int2 e = ring[q * G + j];
+                const int64_t t = tile * G + j;
+                if (t < p.T) {
+                    stream_from_smem<QUANT, OUT>(p, rows_smem + (size_t)(q * G + j) * lay.slot_bytes, e.x, e.y, t, p.out + t * p.D * 2, lane,
+                                                 pol);
+                    flagged |= (e.x < 0 && e.y < 0);
                 }
             }
             __syncwarp();
@@ -257,59 +455,120 @@ static int num_sms() {
     return n;
 }
 
-// Tuning hook (tools/tune_embed.py): SCONE_EMBED_VARIANT="U:MINB" selects another instantiation of the same
-// kernel for the combinations compiled below; anything else runs the default.
-static void variant(int &u, int &minb) {
-    u = 0;
-    minb = 0;
-    if (const char *e = getenv("SCONE_EMBED_VARIANT")) sscanf(e, "%d:%d", &u, &minb);
+// Tuning hook (tools/tune_embed.py): SCONE_EMBED_VARIANT="kind:U:NM:NG:MINB:smemKB" (kind 0 = register loads,
+// 1 = bulk copies) selects another instantiation for the combinations compiled under -DSCONE_TUNE.
+struct Variant {
+    int kind = -1, u = 0, nm = 0, ng = 0, minb = 0, smem_kb = 0;
+};
+static Variant variant() {
+    Variant v;
+    if (const char *e = getenv("SCONE_EMBED_VARIANT")) sscanf(e, "%d:%d:%d:%d:%d:%d", &v.kind, &v.u, &v.nm, &v.ng, &v.minb, &v.smem_kb);
+    return v;
 }
 
-template <int QUANT, int OUT, int P, int U, int MINB>
-static void launch_one(EmbedParams &p, cudaStream_t stream) {
+template <int QUANT, int OUT, int P, int U, int NM, int NG, int MINB>
+static int launch_ldg(EmbedParams &p, cudaStream_t stream) {
     constexpr int G = 32 / P;
     p.num_tiles = (p.T + G - 1) / G;
     const int64_t resident = (int64_t)num_sms() * MINB;
     const unsigned blocks = (unsigned)(p.num_tiles < resident ? p.num_tiles : resident);
-    embed_kernel<QUANT, OUT, P, U, MINB><<<blocks, kThreads, 0, stream>>>(p);
+    embed_kernel<QUANT, OUT, P, U, NM, NG, MINB><<<blocks, 32 * (NM + NG), 0, stream>>>(p);
+    return SCONE_OK;
 }
 
+// Ring geometry for the bulk variant; returns false when rows are too wide for the budget.
+// The ring is a multiple of the matcher count so that every slot is only ever filled by one matcher (mbarrier
+// parity waits are then never more than one phase ahead).
+static bool bulk_layout(const EmbedParams &p, int G, int nm, int budget_bytes, BulkLayout &lay) {
+    int64_t slot = p.row_stride > 2ll * p.D ? p.row_stride : 2ll * p.D;
+    slot = (slot + 127) / 128 * 128;
+    const int64_t per_tile = slot * G;
+    int ring = (int)((budget_bytes - bulk_header_bytes(G)) / per_tile);
+    if (ring > kMaxRing) ring = kMaxRing;
+    ring = ring / nm * nm;
+    if (ring < 2 || ring < nm) return false;
+    lay.ring = ring;
+    lay.slot_bytes = (int)slot;
+    lay.smem_bytes = bulk_header_bytes(G) + (int)(per_tile * ring);
+    return true;
+}
+
+template <int QUANT, int OUT, int P, int NM, int NG, int MINB>
+static int launch_bulk(EmbedParams &p, const BulkLayout &lay, cudaStream_t stream) {
+    constexpr int G = 32 / P;
+    auto kern = embed_bulk_kernel<QUANT, OUT, P, NM, NG, MINB>;
+    static int configured = 0;
+    if (configured < lay.smem_bytes) {
+        SCONE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.smem_bytes));
+        configured = lay.smem_bytes;
+    }
+    p.num_tiles = (p.T + G - 1) / G;
+    const int64_t resident = (int64_t)num_sms() * MINB;
+    const unsigned blocks = (unsigned)(p.num_tiles < resident ? p.num_tiles : resident);
+    kern<<<blocks, 32 * (NM + NG), lay.smem_bytes, stream>>>(p, lay);
+    return SCONE_OK;
+}
+
+// Kernel selection.  Rows that fit the shared-memory ring go through the bulk-copy variant; its shape follows the
+// traffic per position (measured on B200, profiles/tune_r01.md):
+//   narrow rows (<  6 KB moved per position): 4 matcher + 4 gather warps, 3 CTAs/SM, 70 KB ring  -- matcher-hungry
+//   wide rows   (>= 6 KB moved per position): 6 matcher + 12 gather warps, 1 CTA/SM, 200 KB ring -- store-hungry
+// then 2 + 6 warps with a 70 KB ring, and finally the register-load variant for rows too wide for any ring.
 template <int QUANT, int OUT, int P>
-static void launch(EmbedParams &p, cudaStream_t stream) {
-    if constexpr (OUT == SCONE_OUT_BF16 && (P == 4 || P == 8)) {
-        int u, minb;
-        variant(u, minb);
-#define SCONE_V(UU, MM)                                        \
-    if (u == UU && minb == MM) {                               \
-        launch_one<QUANT, OUT, P, UU, MM>(p, stream);          \
-        return;                                                \
-    }
-        SCONE_V(4, 3) SCONE_V(4, 5) SCONE_V(4, 6) SCONE_V(8, 3) SCONE_V(8, 4) SCONE_V(2, 6) SCONE_V(2, 4)
+static int launch(EmbedParams &p, cudaStream_t stream) {
+    constexpr int G = 32 / P;
+    BulkLayout lay;
+#ifdef SCONE_TUNE
+    if constexpr (OUT == SCONE_OUT_BF16 && ((P == 4 && QUANT == SCONE_QUANT_INT8) || (P == 8 && QUANT == SCONE_QUANT_INT4))) {
+        const Variant v = variant();
+#define SCONE_V(UU, NMM, NGG, MM) \
+    if (v.kind == 0 && v.u == UU && v.nm == NMM && v.ng == NGG && v.minb == MM) return launch_ldg<QUANT, OUT, P, UU, NMM, NGG, MM>(p, stream);
+        SCONE_V(4, 4, 8, 3) SCONE_V(2, 4, 8, 4) SCONE_V(4, 1, 8, 4)
 #undef SCONE_V
+#define SCONE_B(NMM, NGG, MM)                                                                                               \
+    if (v.kind == 1 && v.nm == NMM && v.ng == NGG && v.minb == MM && bulk_layout(p, G, NMM, v.smem_kb * 1024, lay))          \
+        return launch_bulk<QUANT, OUT, P, NMM, NGG, MM>(p, lay, stream);
+        SCONE_B(3, 6, 3) SCONE_B(4, 8, 2) SCONE_B(6, 6, 2) SCONE_B(8, 8, 1) SCONE_B(12, 12, 1) SCONE_B(6, 10, 2) SCONE_B(4, 12, 2)
+        SCONE_B(8, 16, 1) SCONE_B(12, 20, 1) SCONE_B(3, 5, 3) SCONE_B(5, 5, 3) SCONE_B(4, 6, 3) SCONE_B(6, 4, 3) SCONE_B(8, 12, 1) SCONE_B(6, 18, 1)
+        SCONE_B(4, 12, 1)
+#undef SCONE_B
+        if (v.kind == 0) return launch_ldg<QUANT, OUT, P, 4, 2, 6, 4>(p, stream);
     }
-    launch_one<QUANT, OUT, P, 4, 4>(p, stream);
+#endif
+    if constexpr (P >= 4) {
+        const int64_t moved = 2ll * p.D + (p.row_stride < 2ll * p.D ? p.row_stride : 2ll * p.D);
+        if (moved >= 6144) {
+            if (bulk_layout(p, G, 6, 200 * 1024, lay)) return launch_bulk<QUANT, OUT, P, 6, 12, 1>(p, lay, stream);
+        } else {
+            if (bulk_layout(p, G, 4, 70 * 1024, lay)) return launch_bulk<QUANT, OUT, P, 4, 4, 3>(p, lay, stream);
+        }
+    }
+    if (bulk_layout(p, G, 2, 70 * 1024, lay)) return launch_bulk<QUANT, OUT, P, 2, 6, 3>(p, lay, stream);
+    return launch_ldg<QUANT, OUT, P, 4, 2, 6, 4>(p, stream);
 }
 
 template <int QUANT, int OUT>
-static void launch_p(int P, EmbedParams &p, cudaStream_t stream) {
+static int launch_p(int P, EmbedParams &p, cudaStream_t stream) {
     switch (P) {
-        case 1: launch<QUANT, OUT, 1>(p, stream); break;
-        case 2: launch<QUANT, OUT, 2>(p, stream); break;
-        case 4: launch<QUANT, OUT, 4>(p, stream); break;
-        default: launch<QUANT, OUT, 8>(p, stream); break;
+        case 1: return launch<QUANT, OUT, 1>(p, stream);
+        case 2: return launch<QUANT, OUT, 2>(p, stream);
+        case 4: return launch<QUANT, OUT, 4>(p, stream);
+        default: return launch<QUANT, OUT, 8>(p, stream);
     }
 }
 
 static int dispatch(int P, EmbedParams &p, int quant, int out_dtype, cudaStream_t stream) {
+    int rc;
     if (out_dtype == SCONE_OUT_BF16) {
-        if (quant == SCONE_QUANT_FP16) launch_p<SCONE_QUANT_FP16, SCONE_OUT_BF16>(P, p, stream);
-        else if (quant == SCONE_QUANT_INT8) launch_p<SCONE_QUANT_INT8, SCONE_OUT_BF16>(P, p, stream);
-        else launch_p<SCONE_QUANT_INT4, SCONE_OUT_BF16>(P, p, stream);
+        if (quant == SCONE_QUANT_FP16) rc = launch_p<SCONE_QUANT_FP16, SCONE_OUT_BF16>(P, p, stream);
+        else if (quant == SCONE_QUANT_INT8) rc = launch_p<SCONE_QUANT_INT8, SCONE_OUT_BF16>(P, p, stream);
+        else rc = launch_p<SCONE_QUANT_INT4, SCONE_OUT_BF16>(P, p, stream);
     } else {
-        if (quant == SCONE_QUANT_FP16) launch_p<SCONE_QUANT_FP16, SCONE_OUT_FP16>(P, p, stream);
-        else if (quant == SCONE_QUANT_INT8) launch_p<SCONE_QUANT_INT8, SCONE_OUT_FP16>(P, p, stream);
-        else launch_p<SCONE_QUANT_INT4, SCONE_OUT_FP16>(P, p, stream);
+        if (quant == SCONE_QUANT_FP16) rc = launch_p<SCONE_QUANT_FP16, SCONE_OUT_FP16>(P, p, stream);
+        else if (quant == SCONE_QUANT_INT8) rc = launch_p<SCONE_QUANT_INT8, SCONE_OUT_FP16>(P, p, stream);
+        else rc = launch_p<SCONE_QUANT_INT4, SCONE_OUT_FP16>(P, p, stream);
     }
+    if (rc != SCONE_OK) return rc;
     SCONE_LAUNCHED();
     return SCONE_OK;
 }

@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(256) lookup_kernel(IndexView ix, const int64_t
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t base = warp * G;
     if (base >= T) return;
-    WindowMatch m = match_window<P>(ix, ids, T, L, base, lane);
+    WindowMatch m = match_window<P>(ix, load_window_token<P>(ids, T, base, lane), T, L, base, lane);
     const int j = lane / P;
     if ((lane % P) == 0 && base + j < T) {
         if (out_id) out_id[base + j] = m.fid;
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(256) match_all_kernel(IndexView ix, const int6
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t base = warp * G;
     if (base >= T) return;
-    int32_t fid = candidate_id<P>(ix, ids, T, L, base, lane, /*use_len_mask=*/true);
+    int32_t fid = candidate_id<P>(ix, load_window_token<P>(ids, T, base, lane), T, L, base, lane, /*use_len_mask=*/true);
     const int j = lane / P, n1 = lane % P;
     if (n1 < ix.max_n && base + j < T) out[(base + j) * ix.max_n + n1] = fid;
 }
@@ -132,7 +132,7 @@ int scone_index_create(const int32_t *d_tokens, const uint8_t *d_lens, int64_t n
     SCONE_REQUIRE(n >= 0 && n < (int64_t)0x7FFFFFFF, "scone_index_create: n = %lld outside [0, 2^31-1)", (long long)n);
     SCONE_REQUIRE(max_n >= 1 && max_n <= SCONE_MAX_N, "scone_index_create: max_n = %d outside [1, %d]", max_n, SCONE_MAX_N);
     SCONE_REQUIRE(n == 0 || (d_tokens && d_lens), "scone_index_create: NULL vocabulary arrays");
-    if (!(load_factor > 0.0)) load_factor = 0.5;
+    if (!(load_factor > 0.0)) load_factor = 0.25;
     SCONE_REQUIRE(load_factor <= 0.9, "scone_index_create: load_factor %.3f > 0.9", load_factor);
 
     scone_index_impl *ix = new (std::nothrow) scone_index_impl();

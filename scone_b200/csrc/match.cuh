@@ -20,19 +20,28 @@ __device__ __forceinline__ int64_t pos_in_row(int64_t i, int64_t L, int64_t T) {
     return i % L;
 }
 
-// id of the candidate this lane is responsible for, or -1.
+// Lanes 0 .. G+P-2 of the warp that owns window `base` hold the tokens base-(P-1) .. base+G-1 (as int32;
+// vocabulary tokens are non-negative int32, anything else is mapped to -1 and can only miss).
 template <int P>
-__device__ __forceinline__ int32_t candidate_id(const IndexView &ix, const int64_t *__restrict__ ids, int64_t T, int64_t L,
-                                                int64_t base, int lane, bool use_len_mask) {
+__device__ __forceinline__ int32_t load_window_token(const int64_t *__restrict__ ids, int64_t T, int64_t base, int lane) {
     constexpr int G = 32 / P;
-    constexpr unsigned FULL = 0xFFFFFFFFu;
-    // lanes 0 .. G+P-2 hold the tokens base-(P-1) .. base+G-1
     const int64_t gi = base - (P - 1) + lane;
     int64_t t64 = -1;
     if (lane < G + P - 1 && gi >= 0 && gi < T) t64 = __ldg(ids + gi);
-    // vocabulary tokens are non-negative int32: anything else can only miss
-    const int32_t tok = (t64 >= 0 && t64 <= 0x7FFFFFFFll) ? (int32_t)t64 : -1;
+    return (t64 >= 0 && t64 <= 0x7FFFFFFFll) ? (int32_t)t64 : -1;
+}
 
+// token of the lane's own position (lane / P) out of the window registers
+template <int P>
+__device__ __forceinline__ int32_t own_token(int32_t tok, int lane) {
+    return __shfl_sync(0xFFFFFFFFu, tok, lane / P + (P - 1));
+}
+
+// id of the candidate this lane is responsible for, or -1.  `tok` from load_window_token.
+template <int P>
+__device__ __forceinline__ int32_t candidate_id(const IndexView &ix, int32_t tok, int64_t T, int64_t L, int64_t base, int lane,
+                                                bool use_len_mask) {
+    constexpr unsigned FULL = 0xFFFFFFFFu;
     const int j = lane / P, n = lane % P + 1;
     const int64_t i = base + j;
     bool cand = n <= ix.max_n && i < T;
@@ -59,10 +68,9 @@ __device__ __forceinline__ int32_t candidate_id(const IndexView &ix, const int64
 
 // Longest hit of the lane's position; every lane of a P-lane group returns the same value.
 template <int P>
-__device__ __forceinline__ WindowMatch match_window(const IndexView &ix, const int64_t *__restrict__ ids, int64_t T, int64_t L,
-                                                    int64_t base, int lane) {
+__device__ __forceinline__ WindowMatch match_window(const IndexView &ix, int32_t tok, int64_t T, int64_t L, int64_t base, int lane) {
     constexpr unsigned FULL = 0xFFFFFFFFu;
-    const int32_t cid = candidate_id<P>(ix, ids, T, L, base, lane, true);
+    const int32_t cid = candidate_id<P>(ix, tok, T, L, base, lane, true);
     const unsigned hit = __ballot_sync(FULL, cid >= 0);
     const int j = lane / P;
     const unsigned bits = (hit >> (j * P)) & ((1u << P) - 1u);

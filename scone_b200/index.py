@@ -27,7 +27,7 @@ class FGramIndex:
     construction, so it can be shared by any number of streams / threads.
     """
 
-    def __init__(self, vocab_tokens: torch.Tensor, vocab_lens: torch.Tensor, load_factor: float = 0.5):
+    def __init__(self, vocab_tokens: torch.Tensor, vocab_lens: torch.Tensor, load_factor: float = 0.25):
         """vocab_tokens int32 [N, max_n] (reading order, padded with -1), vocab_lens uint8 [N]; id = row."""
         _require_cuda(vocab_tokens, "vocab_tokens")
         _require_cuda(vocab_lens, "vocab_lens")

@@ -39,7 +39,8 @@ def graph_time(fn, steps=20, reps=5):
 
 def main():
     name = sys.argv[1] if len(sys.argv) > 1 and not sys.argv[1].startswith("-") else "config2"
-    variants = ["0:0", "4:3", "4:6", "4:8", "8:2", "8:3", "8:4", "2:8", "16:2"]
+    variants = ["-1", "1:0:3:6:3:64", "1:0:4:8:2:100", "1:0:4:8:2:64", "1:0:4:4:3:70", "1:0:6:6:2:100", "1:0:8:8:1:200", "1:0:12:12:1:200",
+                "1:0:6:10:2:100", "1:0:4:12:2:100", "1:0:8:16:1:200", "1:0:12:20:1:200", "1:0:6:12:1:200", "1:0:3:5:3:70", "1:0:2:6:3:70"]
     for a in sys.argv[1:]:
         if a.startswith("--variants="):
             variants = a.split("=", 1)[1].split(",")
@@ -48,7 +49,9 @@ def main():
     B, L, D, N, V = w["B"], w["L"], w["D"], w["N"], w["V"]
     T = B * L
     toks, lens, longest = S.make_vocab_device(N, w["max_n"], V, seed=0, device=dev, return_longest=True)
-    index = sb.FGramIndex(toks, lens)
+    lf = float(os.environ.get("LF", "0.5"))
+    index = sb.FGramIndex(toks, lens, load_factor=lf)
+    print(json.dumps({"load_factor": lf, "index_MB": index.bytes / 1e6, "max_probe": index.max_probe}))
     table = sb.CacheTable(N, D, w["quant"], device=dev)
     S.fill_table_device(table, seed=2)
     base = S.make_base_device(V, D, torch.bfloat16, seed=3, device=dev)
@@ -80,7 +83,7 @@ def main():
     report("gather_only(ids resolved)", graph_time(lambda k: sb.embed_gather(table, base, batches[k % 8], fids[k % 8], out=out)))
     for v in variants:
         os.environ["SCONE_EMBED_VARIANT"] = v
-        report("fused U:MINB=" + v, graph_time(lambda k: sb.embed_forward(index, table, base, batches[k % 8], out=out, out_id=out_id, out_len=out_len)))
+        report("fused kind:U:NM:NG:MINB:KB=" + v, graph_time(lambda k: sb.embed_forward(index, table, base, batches[k % 8], out=out, out_id=out_id, out_len=out_len)))
     os.environ.pop("SCONE_EMBED_VARIANT", None)
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(res, open(f"gpurun_out/tune_{name}.json", "w"), indent=1)
