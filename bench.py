@@ -40,6 +40,12 @@ WORKLOADS = {
                     desc="GPT-2 medium, medium-1m f-grams, max_n=4, INT8 cache, batch 64x1024"),
     "config3": dict(N=10_000_000, D=4096, V=128_000, max_n=5, quant="int4", B=256, L=2048,
                     desc="hidden 4096, 10M f-grams, max_n=5, INT4 g128 cache, batch 256x2048"),
+    # N here is PER GPU (12.5 M rows x 8 192 B = 102 GB per GPU; 100 M f-grams at 8 GPUs)
+    "config4": dict(N=12_500_000, D=4096, V=128_000, max_n=5, quant="fp16", B=256, L=2048, tier="sharded",
+                    desc="hidden 4096, 100M f-grams (12.5M per GPU), FP16 cache row-sharded by id % W via NCCL all-to-all, batch 256x2048 per GPU"),
+    # N is capped by the box's host RAM (pinned); 200 M rows need 416 GB
+    "config5": dict(N=200_000_000, D=2048, V=128_000, max_n=5, quant="int8", B=256, L=2048, tier="host",
+                    desc="hidden 2048, 200M f-grams, INT8 cache in pinned host RAM read zero-copy (TMA bulk over the host link), batch 256x2048"),
 }
 N_BATCHES = 8          # distinct id batches rotated through the timed steps (rows touched >> L2)
 METRIC = "tokens/sec embedded"
@@ -399,6 +405,174 @@ def run_ours(args, w, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+def _tile_fill(table, block_rows=65536, seed=2):
+    """Fill a (possibly huge) table by tiling one quantised random block: same footprint / access pattern as N independent
+    rows at a fraction of the generation time (benchmark data only; parity tests use real tables)."""
+    import torch
+    import scone_b200 as sb
+    from scone_b200.utils import synthetic as S
+    blk = sb.CacheTable(min(block_rows, table.num_rows), table.dim, table.quant, table.group, device=table.device)
+    S.fill_table_device(blk, seed=seed)
+    src = blk.storage
+    for s0 in range(0, table.num_rows, src.shape[0]):
+        k = min(src.shape[0], table.num_rows - s0)
+        table.storage[s0:s0 + k].copy_(src[:k], non_blocking=True)
+    torch.cuda.synchronize()
+
+
+def _timed_steps(step, steps, warmup, barrier, dev, world):
+    import torch
+    import torch.distributed as dist
+    for k in range(max(3, warmup)):
+        step(k)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for k in range(steps):
+        step(k)
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def run_sharded(args, w, rank, local_rank, world):
+    """config 4: table row-sharded over the ranks, ids out / packed rows back over NVLink (scone_b200/sharded.py)."""
+    import torch
+    import torch.distributed as dist
+    import scone_b200 as sb
+    from scone_b200 import _lib, sharded
+    from scone_b200.utils import synthetic as S
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29533")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    B, L, D, V = w["B"], w["L"], w["D"], w["V"]
+    T = B * L
+    rows_per_gpu = args.rows_per_gpu or w["N"]
+    N = rows_per_gpu * world
+    toks, lens, longest = S.make_vocab_device(N, w["max_n"], V, seed=0, device=dev, return_longest=True)
+    index = sb.FGramIndex(toks, lens)
+    table = sb.CacheTable(sharded.shard_rows(N, rank, world), D, w["quant"], device=dev)
+    _tile_fill(table)
+    base = S.make_base_device(V, D, torch.bfloat16, seed=3, device=dev)
+    batches = [S.make_stream_device(toks, lens, B, L, V, seed=100 + rank * N_BATCHES + k, p_plant=1.0, pick_ids=longest) for k in range(4)]
+    del toks, lens, longest
+    torch.cuda.empty_cache()
+    out = torch.empty((B, L, D), dtype=torch.bfloat16, device=dev)
+    cache = sharded.ShardedEmbeddingCache(sharded.CudaOps(index, table, base))
+    l0 = _lib.launch_count()
+    _, fid, _ = cache.lookup(batches[0], out=out)
+    launches_per_step = _lib.launch_count() - l0
+    plan = cache.last_plan
+    hit = float((fid >= 0).float().mean().item())
+    remote = sum(c for r, c in enumerate(plan.send_counts) if r != rank)
+    with ClockSampler(local_rank) as clocks:
+        ms = _timed_steps(lambda k: cache.lookup(batches[k % 4], out=out), args.steps, args.warmup, barrier, dev, world)
+    clk = clocks.summary()
+    if rank == 0:
+        value = world * T * args.steps / (ms * 1e-3)
+        step_s = ms * 1e-3 / args.steps
+        nv_in = remote * (table.row_stride + 4) / step_s / 1e9
+        bpt = bytes_per_token(w, hit, bin(index.len_mask).count("1")) + hit * 2 * table.row_stride   # served copy: read + write once more
+        peak, peak_src = measured_peak_hbm()
+        line = {
+            "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": f"{w['quant']}->bf16", "data": "synthetic",
+            "config": {"workload": w["desc"], "f_grams": N, "rows_per_gpu": rows_per_gpu, "dim": D, "max_n": w["max_n"], "quant": w["quant"],
+                       "per_gpu_batch": [B, L], "parallelism": f"row-sharded x{world}: index replicated, 2 NCCL all-to-alls per step",
+                       "hit_rate": hit, "remote_fraction": remote / max(1, sum(plan.send_counts)), "index_bytes": index.bytes,
+                       "table_bytes_per_gpu": table.bytes, "l2": "inputs > L2 (rows gathered uniformly from the shard)",
+                       "timing": "eager steps (the bucket sizes need one host sync per step), CUDA events, max over ranks"},
+            "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8 * world * 2,
+                    "note": "same call; ids resident on the device, only the all-to-all split sizes cross to the host"},
+            "gpu_launches": int(launches_per_step * args.steps), "clocks": clk,
+            "roofline": {"bound": "hbm", "achieved": bpt * T / step_s / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": bpt * T / step_s / 1e9 / peak, "traffic": None, "peak_source": peak_src, "bytes_per_token": bpt,
+                         "note": "per GPU; this tier is NVLink-bound, see nvlink"},
+            "nvlink": {"achieved_in_GBps_per_gpu": nv_in, "peak": 770.0, "frac": nv_in / 770.0,
+                       "peak_source": "B200_PROFILING.md measured peer copy, per direction per GPU",
+                       "bytes_in_per_step_per_gpu": remote * (table.row_stride + 4)},
+        }
+        print(json.dumps(line), flush=True)
+    dist.destroy_process_group()
+
+
+def run_host(args, w, rank, local_rank, world):
+    """config 5: the table lives in pinned host RAM and is read zero-copy by the same kernels."""
+    import torch
+    import scone_b200 as sb
+    from scone_b200 import _lib
+    from scone_b200.utils import synthetic as S
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    B, L, D, V = w["B"], w["L"], w["D"], w["V"]
+    T = B * L
+    stride, _ = sb.table_layout(w["quant"], D)
+    total_ram = os.sysconf("SC_PAGE_SIZE") * os.sysconf("SC_PHYS_PAGES")
+    budget = int(total_ram * (args.host_fraction or 0.5))
+    N = int(min(w["N"], args.rows_per_gpu or (budget // stride)))
+    t0 = time.perf_counter()
+    table = sb.CacheTable(N, D, w["quant"], device=dev, tier="host")
+    pin_s = time.perf_counter() - t0
+    blk = sb.CacheTable(min(1 << 20, N), D, w["quant"], device=dev)
+    S.fill_table_device(blk, seed=2)
+    for s0 in range(0, N, blk.num_rows):
+        k = min(blk.num_rows, N - s0)
+        table.storage[s0:s0 + k].copy_(blk.storage[:k], non_blocking=True)
+    torch.cuda.synchronize()
+    del blk
+    toks, lens, longest = S.make_vocab_device(N, w["max_n"], V, seed=0, device=dev, return_longest=True)
+    index = sb.FGramIndex(toks, lens)
+    base = S.make_base_device(V, D, torch.bfloat16, seed=3, device=dev)
+    batches = [S.make_stream_device(toks, lens, B, L, V, seed=100 + k, p_plant=1.0, pick_ids=longest) for k in range(4)]
+    del toks, lens, longest
+    out = torch.empty((B, L, D), dtype=torch.bfloat16, device=dev)
+    out_id = torch.empty((B, L), dtype=torch.int32, device=dev)
+    out_len = torch.empty((B, L), dtype=torch.uint8, device=dev)
+
+    def step(k):
+        sb.embed_forward(index, table, base, batches[k % 4], out=out, out_id=out_id, out_len=out_len)
+
+    step(0)
+    hit = float((out_id >= 0).float().mean().item())
+    l0 = _lib.launch_count()
+    with ClockSampler(local_rank) as clocks:
+        ms = _timed_steps(step, args.steps, args.warmup, torch.cuda.synchronize, dev, 1)
+    clk = clocks.summary()
+    step_s = ms * 1e-3 / args.steps
+    link = hit * T * stride / step_s / 1e9
+    line = {
+        "metric": METRIC, "value": T / step_s, "unit": "tokens/s", "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": f"{w['quant']}->bf16", "data": "synthetic",
+        "config": {"workload": w["desc"], "f_grams": N, "f_grams_named": w["N"], "dim": D, "max_n": w["max_n"], "quant": w["quant"],
+                   "batch": [B, L], "hit_rate": hit, "host_ram_bytes": total_ram, "table_bytes_host": table.bytes, "pin_seconds": pin_s,
+                   "scaled": f"N scaled from {w['N']} to {N} rows: the box has {total_ram / 1e9:.0f} GB of host RAM" if N < w["N"] else None,
+                   "tier": "zero-copy: cp.async.bulk straight from pinned host memory into shared memory",
+                   "l2": "rows come over the host link, never cached", "timing": "eager steps, CUDA events"},
+        "e2e": {"value": T / step_s, "unit": "tokens/s", "h2d_bytes_per_step": int(hit * T * stride), "d2h_bytes_per_step": 0,
+                "note": "the row bytes cross the host link inside the kernel (zero-copy)"},
+        "gpu_launches": int(_lib.launch_count() - l0), "clocks": clk,
+        "roofline": {"bound": "hbm", "achieved": link, "peak": 64.0, "unit": "GB/s", "frac": link / 64.0, "traffic": None,
+                     "peak_source": "nominal PCIe Gen5 x16 per direction (host-link bound, not HBM)", "host_link_GBps": link},
+    }
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -407,6 +581,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--rows-per-gpu", type=int, default=0, help="config4/5: table rows per GPU (default: the named size / what host RAM allows)")
+    ap.add_argument("--host-fraction", type=float, default=0.0, help="config5: fraction of host RAM to pin (default 0.5)")
     ap.add_argument("--e2e-embeds-to-host", action="store_true", help="also time e2e with the embeddings copied to pinned host memory")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -420,6 +596,10 @@ def main():
     w = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args, w, rank, world)
+    elif w.get("tier") == "sharded":
+        run_sharded(args, w, rank, local_rank, world)
+    elif w.get("tier") == "host":
+        run_host(args, w, rank, local_rank, world)
     else:
         run_ours(args, w, rank, local_rank, world)
 

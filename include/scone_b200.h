@@ -134,6 +134,12 @@ int scone_table_store(const scone_table_desc_t *table, const float *d_rows_f32, 
 int scone_table_gather(const scone_table_desc_t *table, const int64_t *d_row_ids, int64_t k,
                        void *d_out, int32_t out_dtype, uint32_t *d_status, void *stream);
 
+/* Raw copy of stored rows (no dequant): out[r, :] = the row_stride bytes of table row d_row_ids[r] (int32).
+ * The owner-side step of the row-sharded tier: quantised bytes travel over NVLink and are dequantised by
+ * the requester (scone_embed_gather on the received buffer).  d_out: [k, row_stride] bytes, 16-byte aligned. */
+int scone_table_gather_packed(const scone_table_desc_t *table, const int32_t *d_row_ids, int64_t k,
+                              void *d_out, uint32_t *d_status, void *stream);
+
 /* ---- the fused hot path -----------------------------------------------------
  * One pass replacing, per position: get_token_f_grams + f_gram_to_id + get_embeddings
  * + the engine's assemble loop + the wte fallback

@@ -142,6 +142,36 @@ __global__ void __launch_bounds__(256) gather_kernel(const uint8_t *__restrict__
     }
 }
 
+// One warp per requested row: copy row_stride bytes verbatim (16 B vectors, 4 in flight per lane).
+__global__ void __launch_bounds__(256) gather_packed_kernel(const uint8_t *__restrict__ rows, int64_t row_stride, int64_t num_rows,
+                                                            const int32_t *__restrict__ ids, int64_t k, uint8_t *__restrict__ out,
+                                                            uint32_t *status) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= k) return;
+    const int32_t id = __ldg(ids + r);
+    const bool ok = id >= 0 && id < num_rows;
+    if (!ok && lane == 0 && status) atomicOr(status, SCONE_STATUS_TOKEN_OOR);
+    const uint8_t *src = rows + (int64_t)(ok ? id : 0) * row_stride;
+    uint8_t *dst = out + r * row_stride;
+    const int nvec = (int)(row_stride >> 4);
+    const uint64_t pol = policy_evict_first();
+    for (int c0 = lane; c0 < nvec; c0 += 128) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int c = c0 + 32 * u;
+            v[u] = make_uint4(0u, 0u, 0u, 0u);
+            if (c < nvec && ok) v[u] = ldg_stream_16(src + c * 16, pol);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int c = c0 + 32 * u;
+            if (c < nvec) *reinterpret_cast<uint4 *>(dst + c * 16) = v[u];
+        }
+    }
+}
+
 template <int QUANT>
 static void launch_gather(int out_dtype, unsigned blocks, cudaStream_t stream, const scone_table_desc_t *t, int group_shift,
                           const int64_t *ids, int64_t k, void *out, uint32_t *status) {
@@ -207,6 +237,23 @@ int scone_table_store(const scone_table_desc_t *table, const float *d_rows_f32, 
         store_kernel<SCONE_QUANT_INT8><<<blocks, 256, 0, stream>>>(rows, table->row_stride, table->num_rows, table->dim, 0, table->scale_offset, d_rows_f32, d_row_ids, row_base, k, nullptr);
     else
         store_kernel<SCONE_QUANT_INT4><<<blocks, 256, 0, stream>>>(rows, table->row_stride, table->num_rows, table->dim, table->group, table->scale_offset, d_rows_f32, d_row_ids, row_base, k, nullptr);
+    SCONE_LAUNCHED();
+    return SCONE_OK;
+}
+
+int scone_table_gather_packed(const scone_table_desc_t *table, const int32_t *d_row_ids, int64_t k, void *d_out, uint32_t *d_status,
+                              void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SCONE_REQUIRE(table, "scone_table_gather_packed: NULL table");
+    int rc = check_table(table, "scone_table_gather_packed");
+    if (rc != SCONE_OK) return rc;
+    SCONE_REQUIRE(k >= 0, "scone_table_gather_packed: negative k");
+    if (k == 0) return SCONE_OK;
+    SCONE_REQUIRE(d_row_ids && d_out, "scone_table_gather_packed: NULL buffer");
+    SCONE_REQUIRE(((uintptr_t)d_out & 15) == 0, "scone_table_gather_packed: out must be 16-byte aligned");
+    const unsigned blocks = (unsigned)((k + 7) / 8);
+    gather_packed_kernel<<<blocks, 256, 0, stream>>>(static_cast<const uint8_t *>(table->d_rows), table->row_stride, table->num_rows,
+                                                    d_row_ids, k, static_cast<uint8_t *>(d_out), d_status);
     SCONE_LAUNCHED();
     return SCONE_OK;
 }

@@ -1,0 +1,124 @@
+"""Row-sharded tier: a cache table too large for one GPU, split by f-gram id across the ranks of a process group.
+
+New design (the reference's inference path is single-process, single-GPU).  One process per GPU,
+``torch.distributed`` (NCCL over NVLink 5 / NVSwitch) for the plumbing:
+
+  * the f-gram INDEX is replicated (128 B / f-gram), so every rank matches its own positions locally and only
+    4-byte row numbers travel:  owner(id) = id % W, local row = id // W  (ids are frequency ranks in the reference,
+    ``n_gram_extractor.py:98``, so the modulo spreads the hot low ids over all ranks);
+  * all-to-all #1 carries the requested local row numbers (int32) to their owners;
+  * each owner copies the requested rows VERBATIM -- still quantised -- into a reply buffer (``gather_packed``);
+  * all-to-all #2 carries the packed rows back (INT4: 2 112 B instead of 8 192 B per row over NVLink);
+  * the requester dequantises the received rows, fills misses from its local fallback table and writes
+    ``[B, L, D]`` in one ``scone_embed_gather`` launch.  Misses never leave the GPU.
+
+The routing arithmetic is plain torch (device-agnostic, exercised on CPU with gloo in tests/test_sharded_cpu.py); the
+three compute steps are CUDA kernels of libscone_b200 behind the ``ops`` object.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def owner_of(fgram_id: torch.Tensor, world: int) -> torch.Tensor:
+    return fgram_id % world
+
+
+def local_row_of(fgram_id: torch.Tensor, world: int) -> torch.Tensor:
+    return torch.div(fgram_id, world, rounding_mode="floor")
+
+
+def shard_rows(num_fgrams: int, rank: int, world: int) -> int:
+    """Number of table rows rank ``rank`` owns (ids rank, rank + W, ...)."""
+    return (num_fgrams - rank + world - 1) // world if num_fgrams > rank else 0
+
+
+@dataclass
+class RoutePlan:
+    order: torch.Tensor          # [n_hit] flat positions of the hits, grouped by owner (stable)
+    send_rows: torch.Tensor      # [n_hit] int32 local row numbers, same order
+    send_counts: List[int]       # requests this rank sends to each owner
+    recv_counts: List[int]       # requests this rank receives from each requester
+    slot_of_position: torch.Tensor  # [T] int32: index into the reply buffer, -1 for a miss
+
+
+def make_plan(fgram_id: torch.Tensor, world: int, group=None) -> RoutePlan:
+    """Bucket the hit positions by owner and exchange the bucket sizes (the one host synchronisation of the tier)."""
+    flat = fgram_id.reshape(-1)
+    T = flat.numel()
+    hit = flat >= 0
+    key = torch.where(hit, owner_of(flat.clamp(min=0), world), torch.full_like(flat, world))
+    order_all = torch.argsort(key, stable=True)
+    counts = torch.bincount(key, minlength=world + 1)[:world]
+    n_hit = int(counts.sum().item())
+    order = order_all[:n_hit]
+    send_rows = local_row_of(flat[order], world).to(torch.int32)
+    recv = torch.empty_like(counts)
+    dist.all_to_all_single(recv, counts, group=group)
+    slot = torch.full((T,), -1, dtype=torch.int32, device=flat.device)
+    slot[order] = torch.arange(n_hit, dtype=torch.int32, device=flat.device)
+    return RoutePlan(order, send_rows, counts.tolist(), recv.tolist(), slot)
+
+
+def exchange_requests(plan: RoutePlan, group=None) -> torch.Tensor:
+    """all-to-all #1: local row numbers to their owners.  Returns the int32 rows this rank must serve."""
+    req = torch.empty((sum(plan.recv_counts),), dtype=torch.int32, device=plan.send_rows.device)
+    dist.all_to_all_single(req, plan.send_rows, plan.recv_counts, plan.send_counts, group=group)
+    return req
+
+
+def exchange_replies(plan: RoutePlan, served: torch.Tensor, group=None) -> torch.Tensor:
+    """all-to-all #2: packed rows back to the requesters, in request order.  served: [n_recv, row_stride] uint8."""
+    reply = torch.empty((sum(plan.send_counts), served.shape[1]), dtype=served.dtype, device=served.device)
+    dist.all_to_all_single(reply, served, plan.send_counts, plan.recv_counts, group=group)
+    return reply
+
+
+class CudaOps:
+    """The compute steps, as kernels of libscone_b200."""
+
+    def __init__(self, index, local_table, base_emb: torch.Tensor):
+        self.index, self.table, self.base = index, local_table, base_emb
+
+    def match(self, input_ids: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        return self.index.lookup(input_ids)
+
+    def serve(self, local_rows: torch.Tensor) -> torch.Tensor:
+        return self.table.gather_packed(local_rows)
+
+    def assemble(self, input_ids: torch.Tensor, reply: torch.Tensor, slot_of_position: torch.Tensor,
+                 out: Optional[torch.Tensor]) -> torch.Tensor:
+        from .table import embed_gather
+        view = self.table.view_of(reply) if reply.shape[0] else self.table.view_of(
+            torch.zeros((1, self.table.row_stride), dtype=torch.uint8, device=reply.device))
+        return embed_gather(view, self.base, input_ids, slot_of_position.view(input_ids.shape), out=out)
+
+
+class ShardedEmbeddingCache:
+    """``lookup`` over a table row-sharded across the process group.
+
+    ``ops`` supplies match / serve / assemble; the default is :class:`CudaOps` (there is no CPU implementation in the
+    product -- tests inject an oracle-backed stand-in to exercise the routing on CPU with gloo).
+    """
+
+    def __init__(self, ops, group=None):
+        self.ops = ops
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.last_plan: Optional[RoutePlan] = None
+
+    def lookup(self, input_ids: torch.Tensor, out: Optional[torch.Tensor] = None):
+        fgram_id, match_len = self.ops.match(input_ids)
+        plan = make_plan(fgram_id, self.world, self.group)
+        requests = exchange_requests(plan, self.group)
+        served = self.ops.serve(requests)
+        reply = exchange_replies(plan, served, self.group)
+        embeds = self.ops.assemble(input_ids, reply, plan.slot_of_position, out)
+        self.last_plan = plan
+        return embeds, fgram_id, match_len

@@ -94,6 +94,22 @@ class CacheTable:
         return out
 
 
+    def gather_packed(self, row_ids: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Stored bytes of rows ``row_ids`` (int32) -> uint8 [k, row_stride]; no dequantisation (sharded tier, owner side)."""
+        row_ids = row_ids.to(device=self.device, dtype=torch.int32).contiguous()
+        k = row_ids.numel()
+        if out is None:
+            out = torch.empty((k, self.row_stride), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().scone_table_gather_packed(C.byref(self.desc), row_ids.data_ptr(), k, out.data_ptr(), None,
+                                                             _stream_ptr(self.device)))
+        return out
+
+    def view_of(self, storage: torch.Tensor) -> "CacheTable":
+        """A table with this one's format over another [k, row_stride] uint8 buffer (e.g. rows received from a peer)."""
+        return CacheTable(storage.shape[0], self.dim, self.quant, self.group, self.device, "hbm", storage=storage)
+
+
 def embed_forward(index: FGramIndex, table: CacheTable, base_emb: torch.Tensor, input_ids: torch.Tensor,
                   pos_emb: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
                   status: Optional[torch.Tensor] = None, want_ids: bool = True,

@@ -1,0 +1,54 @@
+"""Multi-GPU parity run of the row-sharded tier (NCCL), launched by torchrun on a box with >= 2 GPUs:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29555 tests/multi_gpu/run_sharded.py
+
+Every rank matches its own batch, the table is split by id % W, and the result must equal the C oracle on the unsharded
+table, bit for bit.  Not collected by pytest (needs several GPUs); gpurun --gpus 2 runs it.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+import scone_b200 as sb  # noqa: E402
+from scone_b200 import sharded  # noqa: E402
+from scone_b200.utils import synthetic as S  # noqa: E402
+from oracle import py_oracle as po  # noqa: E402
+from oracle.c_oracle import COracleIndex  # noqa: E402
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+ok = True
+for quant, D, max_n in (("int4", 4096, 5), ("fp16", 1024, 3), ("int8", 2048, 4)):
+    N, V, B, L = 50_000, 5000, 8, 512
+    toks, lens = S.make_vocab_numpy(N, max_n, V, seed=1)
+    rows = S.make_rows_numpy(N, D, seed=2)
+    base_bits = po.cast_bits(S.make_rows_numpy(V, D, seed=3), "bf16")
+    tab = po.OracleTable.from_fp32(rows, quant)
+    packed, stride, soff = S.pack_table_numpy(quant, tab.payload, tab.scales)
+    q = S.make_stream_numpy(toks, lens, B, L, V, seed=100 + rank)
+    want, wid, wlen, err = COracleIndex(toks, lens).embed(quant, D, 128, packed, stride, packed[:, soff:] if soff else None, stride,
+                                                          base_bits, q, "bf16", nthreads=4)
+    index = sb.FGramIndex(torch.from_numpy(toks).to(dev), torch.from_numpy(lens).to(dev))
+    mine = np.arange(rank, N, world)
+    table = sb.CacheTable(len(mine), D, quant, device=dev)
+    table.store(torch.from_numpy(rows[mine]).to(dev))
+    base = torch.from_numpy(base_bits.view(np.int16).copy()).view(torch.bfloat16).to(dev)
+    cache = sharded.ShardedEmbeddingCache(sharded.CudaOps(index, table, base))
+    emb, fid, ml = cache.lookup(torch.from_numpy(q).to(dev))
+    torch.cuda.synchronize()
+    got = emb.view(torch.int16).cpu().numpy().view(np.uint16)
+    good = np.array_equal(got, want) and np.array_equal(fid.cpu().numpy(), wid) and np.array_equal(ml.cpu().numpy(), wlen)
+    print(f"rank {rank}/{world} {quant} D={D}: {'OK' if good else 'MISMATCH'} hits={int((wid >= 0).sum())} sent={cache.last_plan.send_counts}", flush=True)
+    ok = ok and good
+flag = torch.tensor([0 if ok else 1], device=dev)
+dist.all_reduce(flag)
+dist.destroy_process_group()
+sys.exit(0 if int(flag.item()) == 0 else 1)

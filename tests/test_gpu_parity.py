@@ -412,3 +412,38 @@ def test_input_embedding_module():
     assert emb.shape == (4, 64, 128) and emb.dtype == torch.float16 and torch.equal(fid, fid2)
     want = (plain.float() + wpe.to(DEV).half().float()[None]).half()
     assert (emb.float() - want.float()).abs().max() <= 2e-4      # single vs double rounding: <= 1 fp16 ulp at this scale
+
+
+# ---- row-sharded tier on one GPU (world size 1 over NCCL: exercises CudaOps end to end) ------------------------------
+
+def test_sharded_tier_world1_nccl():
+    import os
+    import torch.distributed as dist
+    sb, S = _mods()
+    from scone_b200 import sharded
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29611")
+    created = not dist.is_initialized()
+    if created:
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device(DEV, 0))
+    try:
+        for quant in ("int4", "fp16"):
+            N, D, V, max_n, B, L = 4000, 512, 300, 5, 3, 130
+            toks, lens = S.make_vocab_numpy(N, max_n, V, seed=41)
+            q = S.make_stream_numpy(toks, lens, B, L, V, seed=42)
+            rows = S.make_rows_numpy(N, D, seed=43)
+            base_bits = po.cast_bits(S.make_rows_numpy(V, D, seed=44), "bf16")
+            want, wid, wlen = po.embed_forward(vocab_dict(toks, lens), max_n, po.OracleTable.from_fp32(rows, quant), base_bits, q, "bf16")
+            ix = _index(toks, lens)
+            t = sb.CacheTable(N, D, quant)
+            t.store(torch.from_numpy(rows).to(DEV))
+            cache = sharded.ShardedEmbeddingCache(sharded.CudaOps(ix, t, _from_bits(base_bits, torch.bfloat16)))
+            emb, fid, ml = cache.lookup(torch.from_numpy(q).to(DEV))
+            assert np.array_equal(fid.cpu().numpy(), wid) and np.array_equal(ml.cpu().numpy(), wlen)
+            assert np.array_equal(_bits(emb), want)
+            # packed gather is a verbatim copy of the stored rows
+            pick = torch.tensor([0, 5, N - 1, 5], dtype=torch.int32, device=DEV)
+            assert torch.equal(t.gather_packed(pick), t.storage[pick.long()])
+    finally:
+        if created:
+            dist.destroy_process_group()
