@@ -479,24 +479,47 @@ def run_sharded(args, w, rank, local_rank, world):
     plan = cache.last_plan
     hit = float((fid >= 0).float().mean().item())
     remote = sum(c for r, c in enumerate(plan.send_counts) if r != rank)
+    mode = args.sharded_mode
+    if mode == "peer":
+        # same shard, now in symmetric memory mapped by every rank; the exchange happens inside the fused kernel
+        ptab = sharded.PeerShardedTable(N, D, w["quant"], device=dev)
+        ptab.local.storage[:table.num_rows].copy_(table.storage)
+        del table, cache
+        torch.cuda.empty_cache()
+        ptab.publish()
+        table = ptab.local
+        out_id = torch.empty((B, L), dtype=torch.int32, device=dev)
+        out_len = torch.empty((B, L), dtype=torch.uint8, device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+
+        def step(k):
+            sharded.embed_forward_sharded(index, ptab, base, batches[k % 4], out=out, status=status, out_id=out_id, out_len=out_len)
+        launches_per_step = 1
+    else:
+        def step(k):
+            cache.lookup(batches[k % 4], out=out)
     with ClockSampler(local_rank) as clocks:
-        ms = _timed_steps(lambda k: cache.lookup(batches[k % 4], out=out), args.steps, args.warmup, barrier, dev, world)
+        ms = _timed_steps(step, args.steps, args.warmup, barrier, dev, world)
     clk = clocks.summary()
     if rank == 0:
         value = world * T * args.steps / (ms * 1e-3)
         step_s = ms * 1e-3 / args.steps
         nv_in = remote * (table.row_stride + 4) / step_s / 1e9
-        bpt = bytes_per_token(w, hit, bin(index.len_mask).count("1")) + hit * 2 * table.row_stride   # served copy: read + write once more
+        bpt = bytes_per_token(w, hit, bin(index.len_mask).count("1"))
+        if mode != "peer":
+            bpt += hit * 2 * table.row_stride                    # NCCL variant: served copy is read + written once more
         peak, peak_src = measured_peak_hbm()
         line = {
             "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": f"{w['quant']}->bf16", "data": "synthetic",
             "config": {"workload": w["desc"], "f_grams": N, "rows_per_gpu": rows_per_gpu, "dim": D, "max_n": w["max_n"], "quant": w["quant"],
-                       "per_gpu_batch": [B, L], "parallelism": f"row-sharded x{world}: index replicated, 2 NCCL all-to-alls per step",
+                       "per_gpu_batch": [B, L], "parallelism": (f"row-sharded x{world}: index replicated, rows pulled from peer memory over NVLink inside the fused kernel (TMA bulk)"
+                                       if mode == "peer" else f"row-sharded x{world}: index replicated, 2 NCCL all-to-alls per step"),
                        "hit_rate": hit, "remote_fraction": remote / max(1, sum(plan.send_counts)), "index_bytes": index.bytes,
                        "table_bytes_per_gpu": table.bytes, "l2": "inputs > L2 (rows gathered uniformly from the shard)",
-                       "timing": "eager steps (the bucket sizes need one host sync per step), CUDA events, max over ranks"},
+                       "sharded_mode": mode,
+                       "timing": "eager steps, CUDA events, max over ranks"},
             "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8 * world * 2,
                     "note": "same call; ids resident on the device, only the all-to-all split sizes cross to the host"},
             "gpu_launches": int(launches_per_step * args.steps), "clocks": clk,
@@ -582,6 +605,7 @@ def main():
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--rows-per-gpu", type=int, default=0, help="config4/5: table rows per GPU (default: the named size / what host RAM allows)")
+    ap.add_argument("--sharded-mode", default="peer", choices=["peer", "nccl"], help="config4: peer-direct fused kernel or NCCL all-to-all")
     ap.add_argument("--host-fraction", type=float, default=0.0, help="config5: fraction of host RAM to pin (default 0.5)")
     ap.add_argument("--e2e-embeds-to-host", action="store_true", help="also time e2e with the embeddings copied to pinned host memory")
     args = ap.parse_args()

@@ -168,6 +168,21 @@ int scone_embed_gather(const scone_table_desc_t *table, const void *d_base_emb, 
                        const int64_t *d_ids, const int32_t *d_fgram_id, int64_t T,
                        void *d_out, int32_t out_dtype, uint32_t *d_status, void *stream);
 
+/* Row-sharded table read DIRECTLY over NVLink (peer memory), fused into the same kernel: f-gram id r lives on rank
+ * r % world, at row r / world of that rank's shard.  d_shard_rows is a DEVICE array of `world` pointers to the
+ * shards as mapped into THIS process (peer-mapped allocations, e.g. torch symmetric-memory buffer_ptrs; entry
+ * `rank` is the local shard).  `shard` describes the common row geometry (row_stride, quant, dim, ...; its d_rows is
+ * ignored, its num_rows is the capacity of one shard); total_rows = number of f-gram rows over all shards.
+ * The matcher warps turn (owner, local row) into a peer address and the TMA bulk copy / vector loads fetch the still
+ * quantised row across NVSwitch straight into shared memory; no request/reply exchange, no host synchronisation, and
+ * misses never leave the GPU.  Everything else is scone_embed_forward. */
+int scone_embed_forward_sharded(const scone_index_t *index, const scone_table_desc_t *shard,
+                                const void *const *d_shard_rows, int32_t world, int64_t total_rows,
+                                const void *d_base_emb, int64_t base_rows, const void *d_pos_emb,
+                                const int64_t *d_ids, int64_t B, int64_t L,
+                                void *d_out, int32_t out_dtype,
+                                int32_t *d_out_id, uint8_t *d_out_len, uint32_t *d_status, void *stream);
+
 /* Number of kernels this library has launched from the calling process (monotonic). */
 int64_t scone_launch_count(void);
 

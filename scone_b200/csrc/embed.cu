@@ -28,6 +28,7 @@ struct EmbedParams {
     IndexView ix;
     const int32_t *fgram_in;  // not NULL: ids already resolved, the matcher only forwards them
     const uint8_t *rows;
+    const uint8_t *const *shard_rows;  // world > 1: peer-mapped shard base pointers (device array), row r on shard r % world
     int64_t row_stride;
     int64_t num_rows;
     const uint8_t *base;  // [V, D] 16-bit
@@ -43,7 +44,17 @@ struct EmbedParams {
     int32_t D;
     int32_t scale_off;
     int32_t group_shift;  // log2(group / 8): chunk index >> group_shift = group index (INT4)
+    int32_t world;        // 1 = the whole table is at `rows`
 };
+
+// address of table row `fid`: local, or on the peer that owns it (NVLink)
+__device__ __forceinline__ const uint8_t *row_ptr(const EmbedParams &p, int32_t fid) {
+    if (p.world == 1) return p.rows + (int64_t)fid * p.row_stride;
+    const int32_t w = p.world < 0 ? -p.world : p.world;  // negative: sharded, read through the pointer table
+    const int32_t owner = fid % w, local = fid / w;
+    const uint8_t *base = reinterpret_cast<const uint8_t *>(__ldg(reinterpret_cast<const unsigned long long *>(p.shard_rows) + owner));
+    return base + (int64_t)local * p.row_stride;
+}
 
 constexpr int kRing = 16;  // tiles the matchers may run ahead of the gather warps
 
@@ -62,7 +73,7 @@ __device__ __forceinline__ uint4 pack16x8(const float (&x)[8]) {
 // Hit: dequantise table row `fid` into dst.  U 256-element steps in flight per lane.
 template <int QUANT, int OUT, int U>
 __device__ __forceinline__ void stream_hit(const EmbedParams &p, int32_t fid, uint8_t *__restrict__ dst, int lane, uint64_t pol) {
-    const uint8_t *__restrict__ row = p.rows + (int64_t)fid * p.row_stride;
+    const uint8_t *__restrict__ row = row_ptr(p, fid);
     const int nchunks = p.D >> 3;
     float rs = 1.0f;
     if (QUANT == SCONE_QUANT_INT8) rs = __ldg(reinterpret_cast<const float *>(row + p.scale_off));
@@ -131,7 +142,7 @@ template <int QUANT, int OUT>
 __device__ __noinline__ void stream_general(const EmbedParams &p, int32_t fid, int32_t tok, int64_t t, uint8_t *__restrict__ dst,
                                             int lane) {
     const int nchunks = p.D >> 3;
-    const uint8_t *row = fid >= 0 ? p.rows + (int64_t)fid * p.row_stride : nullptr;
+    const uint8_t *row = fid >= 0 ? row_ptr(p, fid) : nullptr;
     const uint8_t *brow = (fid < 0 && tok >= 0) ? p.base + (int64_t)tok * p.D * 2 : nullptr;
     const uint8_t *prow = p.pos ? p.pos + pos_in_row(t, p.L, p.T) * p.D * 2 : nullptr;
     for (int c = lane; c < nchunks; c += 32) {
@@ -408,7 +419,7 @@ __global__ void __launch_bounds__(32 * (NM + NG), MINB) embed_bulk_kernel(const 
             uint32_t bytes = 0;
             if (owner) {
                 if (fid >= 0) {
-                    src = p.rows + (int64_t)fid * p.row_stride;
+                    src = row_ptr(p, fid);
                     bytes = (uint32_t)p.row_stride;
                 } else if (tok >= 0) {
                     src = p.base + (int64_t)tok * p.D * 2;
@@ -605,6 +616,8 @@ static int fill_table(EmbedParams &p, const scone_table_desc_t *t, const char *w
     int rc = check_table(t, who);
     if (rc != SCONE_OK) return rc;
     p.rows = static_cast<const uint8_t *>(t->d_rows);
+    p.shard_rows = nullptr;
+    p.world = 1;
     p.row_stride = t->row_stride;
     p.num_rows = t->num_rows;
     p.D = t->dim;
@@ -657,6 +670,51 @@ int scone_embed_forward(const scone_index_t *index, const scone_table_desc_t *ta
     p.out_len = d_out_len;
     p.status = d_status;
     return dispatch(lanes_per_token(ix->max_n), p, table->quant, out_dtype, stream);
+}
+
+int scone_embed_forward_sharded(const scone_index_t *index, const scone_table_desc_t *shard, const void *const *d_shard_rows,
+                                int32_t world, int64_t total_rows, const void *d_base_emb, int64_t base_rows, const void *d_pos_emb,
+                                const int64_t *d_ids, int64_t B, int64_t L, void *d_out, int32_t out_dtype, int32_t *d_out_id,
+                                uint8_t *d_out_len, uint32_t *d_status, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SCONE_REQUIRE(index && shard && d_shard_rows, "scone_embed_forward_sharded: NULL index, shard descriptor or pointer table");
+    SCONE_REQUIRE(world >= 1 && world <= 64, "scone_embed_forward_sharded: world %d outside [1, 64]", world);
+    SCONE_REQUIRE(out_dtype == SCONE_OUT_BF16 || out_dtype == SCONE_OUT_FP16, "scone_embed_forward_sharded: out_dtype must be bf16 or fp16");
+    SCONE_REQUIRE(B >= 0 && L >= 0, "scone_embed_forward_sharded: negative shape");
+    const int64_t T = B * L;
+    if (T == 0) return SCONE_OK;
+    SCONE_REQUIRE(T < (1ll << 40), "scone_embed_forward_sharded: batch too large");
+    SCONE_REQUIRE(d_ids && d_out, "scone_embed_forward_sharded: NULL ids or out");
+    SCONE_REQUIRE(d_base_emb && base_rows > 0, "scone_embed_forward_sharded: base embedding table required (fallback rows)");
+    SCONE_REQUIRE((((uintptr_t)d_base_emb | (uintptr_t)d_out | (uintptr_t)d_pos_emb) & 15) == 0,
+                  "scone_embed_forward_sharded: base_emb, pos_emb and out must be 16-byte aligned");
+    const scone_index_impl *ix = reinterpret_cast<const scone_index_impl *>(index);
+    SCONE_REQUIRE(ix->n <= total_rows, "scone_embed_forward_sharded: index has %lld f-grams but the shards only %lld rows", (long long)ix->n,
+                  (long long)total_rows);
+    SCONE_REQUIRE((total_rows + world - 1) / world <= shard->num_rows, "scone_embed_forward_sharded: %lld rows over %d shards exceed the shard capacity %lld",
+                  (long long)total_rows, world, (long long)shard->num_rows);
+    EmbedParams p{};
+    scone_table_desc_t geom = *shard;
+    if (!geom.d_rows) geom.d_rows = reinterpret_cast<const void *>(uintptr_t(16));  // geometry only; never dereferenced when world > 1
+    int rc = fill_table(p, &geom, "scone_embed_forward_sharded");
+    if (rc != SCONE_OK) return rc;
+    p.shard_rows = reinterpret_cast<const uint8_t *const *>(d_shard_rows);
+    p.rows = nullptr;
+    p.num_rows = total_rows;
+    p.ix = IndexView{ix->slots, ix->cap, ix->len_mask, ix->max_n};
+    p.fgram_in = nullptr;
+    p.base = static_cast<const uint8_t *>(d_base_emb);
+    p.V = base_rows;
+    p.pos = static_cast<const uint8_t *>(d_pos_emb);
+    p.ids = d_ids;
+    p.T = T;
+    p.L = L;
+    p.out = static_cast<uint8_t *>(d_out);
+    p.out_id = d_out_id;
+    p.out_len = d_out_len;
+    p.status = d_status;
+    p.world = -world;  // negative: always go through the pointer table, even for one shard
+    return dispatch(lanes_per_token(ix->max_n), p, shard->quant, out_dtype, stream);
 }
 
 int scone_embed_gather(const scone_table_desc_t *table, const void *d_base_emb, int64_t base_rows, const void *d_pos_emb,

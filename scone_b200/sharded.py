@@ -122,3 +122,78 @@ class ShardedEmbeddingCache:
         embeds = self.ops.assemble(input_ids, reply, plan.slot_of_position, out)
         self.last_plan = plan
         return embeds, fgram_id, match_len
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Peer-direct variant: the gather and the exchange are ONE kernel.  Every rank maps every shard (symmetric memory over
+# NVLink / NVSwitch); the matcher warps of the fused kernel turn (id % W, id // W) into a peer address and the TMA bulk
+# copy pulls the still-quantised row across NVSwitch straight into shared memory.  No request / reply messages, no
+# bucketing, no host synchronisation -- the call is CUDA-graph capturable like the single-GPU path.
+# ----------------------------------------------------------------------------------------------------------------
+
+class PeerShardedTable:
+    """This rank's shard of a table of ``total_rows`` rows, allocated in symmetric memory and mapped by all peers."""
+
+    def __init__(self, total_rows: int, dim: int, quant: str = "fp16", group_size: int = 128, device=None, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        from .table import CacheTable, table_layout
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.total_rows = int(total_rows)
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        cap = (self.total_rows + self.world - 1) // self.world
+        row_stride, _ = table_layout(quant, dim, group_size)
+        try:
+            symm_mem.enable_symm_mem_for_group(self.group.group_name)
+        except Exception:
+            pass
+        storage = symm_mem.empty((max(cap, 1), row_stride), dtype=torch.uint8, device=self.device)
+        storage.zero_()
+        self._handle = symm_mem.rendezvous(storage, self.group.group_name)
+        self.local = CacheTable(max(cap, 1), dim, quant, group_size, self.device, storage=storage)
+        self.ptr_table = torch.tensor(list(self._handle.buffer_ptrs), dtype=torch.int64, device=self.device)
+        self.rows_owned = shard_rows(self.total_rows, self.rank, self.world)
+
+    def store_owned(self, rows_fp32: torch.Tensor, fgram_ids: torch.Tensor) -> None:
+        """Quantise and store the rows of the given GLOBAL f-gram ids; ids this rank does not own are ignored."""
+        fgram_ids = fgram_ids.to(self.device)
+        mine = owner_of(fgram_ids, self.world) == self.rank
+        if bool(mine.any()):
+            self.local.store(rows_fp32.to(self.device)[mine], local_row_of(fgram_ids[mine], self.world))
+
+    def publish(self) -> None:
+        """Make this rank's rows visible to its peers (call once after the last store)."""
+        torch.cuda.synchronize(self.device)
+        dist.barrier(self.group)
+
+
+def embed_forward_sharded(index, table: PeerShardedTable, base_emb: torch.Tensor, input_ids: torch.Tensor,
+                          pos_emb: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+                          status: Optional[torch.Tensor] = None, out_id: Optional[torch.Tensor] = None,
+                          out_len: Optional[torch.Tensor] = None):
+    """The fused hot path over a peer-mapped, row-sharded table (one kernel, asynchronous, graph-capturable)."""
+    import ctypes as C
+    from . import _lib
+    from .index import _stream_ptr
+    from .table import _OUT
+    ids = index._check_ids(input_ids)
+    B, L = ids.shape
+    dev = index.device
+    D = table.local.dim
+    if base_emb.dtype not in (torch.bfloat16, torch.float16) or base_emb.dim() != 2 or base_emb.shape[1] != D \
+            or not base_emb.is_contiguous() or base_emb.device != dev:
+        raise ValueError(f"base_emb must be contiguous bf16/fp16 [V, {D}] on {dev}")
+    if out is None:
+        out = torch.empty((B, L, D), dtype=base_emb.dtype, device=dev)
+    if out_id is None:
+        out_id = torch.empty((B, L), dtype=torch.int32, device=dev)
+    if out_len is None:
+        out_len = torch.empty((B, L), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().scone_embed_forward_sharded(
+            index.handle, C.byref(table.local.desc), table.ptr_table.data_ptr(), table.world, table.total_rows,
+            base_emb.data_ptr(), base_emb.shape[0], pos_emb.data_ptr() if pos_emb is not None else None,
+            ids.data_ptr(), B, L, out.data_ptr(), _OUT[base_emb.dtype], out_id.data_ptr(), out_len.data_ptr(),
+            status.data_ptr() if status is not None else None, _stream_ptr(dev)))
+    return out, out_id, out_len

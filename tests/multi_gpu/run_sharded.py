@@ -48,6 +48,19 @@ for quant, D, max_n in (("int4", 4096, 5), ("fp16", 1024, 3), ("int8", 2048, 4))
     good = np.array_equal(got, want) and np.array_equal(fid.cpu().numpy(), wid) and np.array_equal(ml.cpu().numpy(), wlen)
     print(f"rank {rank}/{world} {quant} D={D}: {'OK' if good else 'MISMATCH'} hits={int((wid >= 0).sum())} sent={cache.last_plan.send_counts}", flush=True)
     ok = ok and good
+    # peer-direct variant: one kernel, rows pulled over NVLink from symmetric memory
+    pt = sharded.PeerShardedTable(N, D, quant, device=dev)
+    pt.store_owned(torch.from_numpy(rows[mine]), torch.from_numpy(mine))
+    pt.publish()
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    emb2, fid2, ml2 = sharded.embed_forward_sharded(index, pt, base, torch.from_numpy(q).to(dev), status=status)
+    torch.cuda.synchronize()
+    dist.barrier()
+    got2 = emb2.view(torch.int16).cpu().numpy().view(np.uint16)
+    good2 = np.array_equal(got2, want) and np.array_equal(fid2.cpu().numpy(), wid) and np.array_equal(ml2.cpu().numpy(), wlen) \
+        and int(status.item()) == 0
+    print(f"rank {rank}/{world} {quant} D={D} peer-direct: {'OK' if good2 else 'MISMATCH'}", flush=True)
+    ok = ok and good2
 flag = torch.tensor([0 if ok else 1], device=dev)
 dist.all_reduce(flag)
 dist.destroy_process_group()

@@ -1,7 +1,9 @@
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=index,name --format=csv,noheader
 N=${NGPU:-2}
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29555 tests/multi_gpu/run_sharded.py > gpurun_out/sharded_parity_n$N.log 2>&1; echo "sharded parity rc=$?"; grep -E "rank|Error|error" gpurun_out/sharded_parity_n$N.log | tail -12
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29556 bench.py --gpus $N --workload config4 --steps 10 --warmup 3 --rows-per-gpu ${ROWS:-2500000} > gpurun_out/bench_config4_n$N.json 2> gpurun_out/bench_config4_n$N.err; echo "config4 rc=$?"; grep metric gpurun_out/bench_config4_n$N.json | cut -c1-2500; tail -3 gpurun_out/bench_config4_n$N.err
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29557 bench.py --gpus $N --steps 50 --warmup 5 > gpurun_out/bench_config2_n$N.json 2> gpurun_out/bench_config2_n$N.err; echo "config2 rc=$?"; grep metric gpurun_out/bench_config2_n$N.json | cut -c1-400
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29558 bench.py --gpus $N --workload config3 --steps 20 --warmup 3 > gpurun_out/bench_config3_n$N.json 2> gpurun_out/bench_config3_n$N.err; echo "config3 rc=$?"; grep metric gpurun_out/bench_config3_n$N.json | cut -c1-400
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29555 tests/multi_gpu/run_sharded.py > gpurun_out/sharded_parity_n$N.log 2>&1; echo "sharded parity rc=$?"; grep -E "rank|Error|error" gpurun_out/sharded_parity_n$N.log | tail -14
+for MODE in peer nccl; do
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29556 bench.py --gpus $N --workload config4 --steps 10 --warmup 3 --rows-per-gpu ${ROWS:-2500000} --sharded-mode $MODE > gpurun_out/bench_config4_${MODE}_n$N.json 2> gpurun_out/bench_config4_${MODE}_n$N.err; echo "config4 $MODE rc=$?"; grep metric gpurun_out/bench_config4_${MODE}_n$N.json | python -c "
+import json,sys
+for l in sys.stdin:
+    d=json.loads(l); print(d['config']['sharded_mode'], 'Mtok/s', round(d['value']/1e6,1), 'ms/step', round(d['ms_per_step'],3), 'nvlink GB/s/GPU', round(d['nvlink']['achieved_in_GBps_per_gpu'],1), 'hbm frac', round(d['roofline']['frac'],3))"; tail -2 gpurun_out/bench_config4_${MODE}_n$N.err | cut -c1-300
+done
