@@ -144,10 +144,6 @@ class PeerShardedTable:
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         cap = (self.total_rows + self.world - 1) // self.world
         row_stride, _ = table_layout(quant, dim, group_size)
-        try:
-            symm_mem.enable_symm_mem_for_group(self.group.group_name)
-        except Exception:
-            pass
         storage = symm_mem.empty((max(cap, 1), row_stride), dtype=torch.uint8, device=self.device)
         storage.zero_()
         self._handle = symm_mem.rendezvous(storage, self.group.group_name)
