@@ -183,6 +183,13 @@ int scone_embed_forward_sharded(const scone_index_t *index, const scone_table_de
                                 void *d_out, int32_t out_dtype,
                                 int32_t *d_out_id, uint8_t *d_out_len, uint32_t *d_status, void *stream);
 
+/* Offloaded tier, STAGED variant (host code, no GPU work): copy rows h_row_ids[0..k) of a host-resident table into a
+ * contiguous pinned staging buffer with `nthreads` host threads, ready for one cudaMemcpyAsync.  The zero-copy
+ * variant needs nothing special: point scone_table_desc_t.d_rows at the pinned (UVA-mapped) table.
+ * Returns SCONE_E_INVALID if an id is outside [0, num_rows). */
+int scone_host_gather_rows(const void *h_rows, int64_t row_stride, int64_t num_rows, const int32_t *h_row_ids,
+                           int64_t k, void *h_staging, int32_t nthreads);
+
 /* Number of kernels this library has launched from the calling process (monotonic). */
 int64_t scone_launch_count(void);
 

@@ -447,3 +447,28 @@ def test_sharded_tier_world1_nccl():
     finally:
         if created:
             dist.destroy_process_group()
+
+
+def test_offloaded_tier_zero_copy_and_staged():
+    """Pinned-host table: zero-copy through the fused kernel, and the staged (host gather + async copy) variant."""
+    sb, S = _mods()
+    from scone_b200.offload import StagedHostLookup
+    N, D, V, max_n, B, L = 6000, 1024, 400, 5, 8, 300
+    toks, lens = S.make_vocab_numpy(N, max_n, V, seed=51)
+    q = S.make_stream_numpy(toks, lens, B, L, V, seed=52)
+    rows = S.make_rows_numpy(N, D, seed=53)
+    base_bits = po.cast_bits(S.make_rows_numpy(V, D, seed=54), "bf16")
+    want, wid, wlen = po.embed_forward(vocab_dict(toks, lens), max_n, po.OracleTable.from_fp32(rows, "int8"), base_bits, q, "bf16")
+    ix = _index(toks, lens)
+    host = sb.CacheTable(N, D, "int8", tier="host")
+    host.store(torch.from_numpy(rows).to(DEV))
+    torch.cuda.synchronize()
+    base = _from_bits(base_bits, torch.bfloat16)
+    out, fid, ml = sb.embed_forward(ix, host, base, torch.from_numpy(q).to(DEV))
+    assert np.array_equal(fid.cpu().numpy(), wid) and np.array_equal(_bits(out), want)
+    for m in (1, 3, 4):
+        st = StagedHostLookup(ix, host, base, micro_batches=m, max_positions=B * L, threads=4)
+        out2, fid2, ml2 = st.lookup(torch.from_numpy(q).to(DEV))
+        torch.cuda.synchronize()
+        assert np.array_equal(fid2.cpu().numpy(), wid) and np.array_equal(ml2.cpu().numpy(), wlen)
+        assert np.array_equal(_bits(out2), want)
