@@ -168,6 +168,16 @@ int scone_embed_gather(const scone_table_desc_t *table, const void *d_base_emb, 
                        const int64_t *d_ids, const int32_t *d_fgram_id, int64_t T,
                        void *d_out, int32_t out_dtype, uint32_t *d_status, void *stream);
 
+/* Optional mode reproducing the reference CODE instead of Algorithm 2: the engine's assemble loop
+ * (scone/inference/engine.py:235-259) -- out[b, i] = mean of dequant(row) over ALL f-grams that CONTAIN position i
+ * (list order of get_token_f_grams, n_gram_extractor.py:119-124: n ascending, then start ascending; fp32 sum in that
+ * order, divided by the count), ZEROS where there is none.  No fallback row, no replacement: the reference adds this
+ * (projected) tensor to wte(input_ids) afterwards (language_model.py:236-243).
+ * d_work: int32 [B, L, max_n] scratch (filled with scone_index_match_all's result).  out_dtype may be FP32. */
+int scone_embed_mean_forward(const scone_index_t *index, const scone_table_desc_t *table,
+                             const int64_t *d_ids, int64_t B, int64_t L, int32_t *d_work,
+                             void *d_out, int32_t out_dtype, void *stream);
+
 /* Row-sharded table read DIRECTLY over NVLink (peer memory), fused into the same kernel: f-gram id r lives on rank
  * r % world, at row r / world of that rank's shard.  d_shard_rows is a DEVICE array of `world` pointers to the
  * shards as mapped into THIS process (peer-mapped allocations, e.g. torch symmetric-memory buffer_ptrs; entry

@@ -23,7 +23,7 @@ SYMBOLS = [
     "scone_version", "scone_last_error", "scone_launch_count", "scone_host_gather_rows",
     "scone_index_create", "scone_index_destroy", "scone_index_info", "scone_index_lookup", "scone_index_match_all",
     "scone_table_layout", "scone_table_store", "scone_table_gather", "scone_table_gather_packed",
-    "scone_embed_forward", "scone_embed_gather", "scone_embed_forward_sharded",
+    "scone_embed_forward", "scone_embed_gather", "scone_embed_forward_sharded", "scone_embed_mean_forward",
 ]
 
 
@@ -72,6 +72,7 @@ def load() -> C.CDLL:
     L.scone_host_gather_rows.argtypes = [vp, i64, i64, vp, i64, vp, i32]
     L.scone_embed_forward.argtypes = [vp, C.POINTER(TableDesc), vp, i64, vp, vp, i64, i64, vp, i32, vp, vp, vp, vp]
     L.scone_embed_forward_sharded.argtypes = [vp, C.POINTER(TableDesc), vp, i32, i64, vp, i64, vp, vp, i64, i64, vp, i32, vp, vp, vp, vp]
+    L.scone_embed_mean_forward.argtypes = [vp, C.POINTER(TableDesc), vp, i64, i64, vp, vp, i32, vp]
     L.scone_embed_gather.argtypes = [C.POINTER(TableDesc), vp, i64, vp, i64, vp, vp, i64, vp, i32, vp, vp]
     for name in SYMBOLS:
         fn = getattr(L, name)

@@ -172,6 +172,76 @@ __global__ void __launch_bounds__(256) gather_packed_kernel(const uint8_t *__res
     }
 }
 
+// Reference-code semantics: one warp per position, mean of the rows of every f-gram containing it.
+// all_ids[t, n-1] = id of the n-gram ENDING at flat position t (scone_index_match_all).
+template <int QUANT, int OUT>
+__global__ void __launch_bounds__(256) mean_kernel(const uint8_t *__restrict__ rows, int64_t row_stride, int D, int group_shift,
+                                                   int scale_off, const int32_t *__restrict__ all_ids, int max_n, int64_t T, int64_t L,
+                                                   uint8_t *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (t >= T) return;
+    const int64_t pos = t % L;
+    // the containing f-grams, in the reference's list order: n ascending, start ascending
+    int32_t ids[28];
+    int k = 0;
+    for (int n = 1; n <= max_n; ++n) {
+        for (int s = n - 1; s >= 0; --s) {  // start = pos - s ascending  <=>  end = pos - s + n - 1 ascending
+            const int64_t e = pos - s + n - 1;
+            if (pos - s < 0 || e >= L) continue;
+            const int32_t id = __ldg(all_ids + (t - s + n - 1) * max_n + (n - 1));
+            if (id >= 0) ids[k++] = id;
+        }
+    }
+    const int nchunks = D >> 3;
+    constexpr int OB = OUT == SCONE_OUT_FP32 ? 4 : 2;
+    for (int c = lane; c < nchunks; c += 32) {
+        float acc[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = 0.0f;
+        for (int r = 0; r < k; ++r) {
+            const uint8_t *row = rows + (int64_t)ids[r] * row_stride;
+            float x[8];
+            if (QUANT == SCONE_QUANT_FP16) {
+                decode_fp16x8(ldg_stream_16(row + c * 16), x);
+            } else if (QUANT == SCONE_QUANT_INT8) {
+                decode_int8x8(ldg_stream_8(row + c * 8), __ldg(reinterpret_cast<const float *>(row + scale_off)), x);
+            } else {
+                const __half hs = __ldg(reinterpret_cast<const __half *>(row + scale_off) + (c >> group_shift));
+                decode_int4x8(ldg_stream_4(row + c * 4), __half2float(hs), x);
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] = __fadd_rn(acc[e], x[e]);
+        }
+        if (k > 1) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] = __fdiv_rn(acc[e], (float)k);
+        }
+        uint8_t *o = out + (t * D + c * 8) * OB;
+        if (OUT == SCONE_OUT_FP32) {
+            *reinterpret_cast<float4 *>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            *reinterpret_cast<float4 *>(o + 16) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        } else if (OUT == SCONE_OUT_BF16) {
+            *reinterpret_cast<uint4 *>(o) = pack_bf16x8(acc);
+        } else {
+            *reinterpret_cast<uint4 *>(o) = pack_fp16x8(acc);
+        }
+    }
+}
+
+template <int QUANT>
+static void launch_mean(int out_dtype, unsigned blocks, cudaStream_t stream, const scone_table_desc_t *t, int group_shift,
+                        const int32_t *all_ids, int max_n, int64_t T, int64_t L, void *out) {
+    const uint8_t *rows = static_cast<const uint8_t *>(t->d_rows);
+    uint8_t *o = static_cast<uint8_t *>(out);
+    if (out_dtype == SCONE_OUT_FP32)
+        mean_kernel<QUANT, SCONE_OUT_FP32><<<blocks, 256, 0, stream>>>(rows, t->row_stride, t->dim, group_shift, t->scale_offset, all_ids, max_n, T, L, o);
+    else if (out_dtype == SCONE_OUT_BF16)
+        mean_kernel<QUANT, SCONE_OUT_BF16><<<blocks, 256, 0, stream>>>(rows, t->row_stride, t->dim, group_shift, t->scale_offset, all_ids, max_n, T, L, o);
+    else
+        mean_kernel<QUANT, SCONE_OUT_FP16><<<blocks, 256, 0, stream>>>(rows, t->row_stride, t->dim, group_shift, t->scale_offset, all_ids, max_n, T, L, o);
+}
+
 template <int QUANT>
 static void launch_gather(int out_dtype, unsigned blocks, cudaStream_t stream, const scone_table_desc_t *t, int group_shift,
                           const int64_t *ids, int64_t k, void *out, uint32_t *status) {
@@ -237,6 +307,32 @@ int scone_table_store(const scone_table_desc_t *table, const float *d_rows_f32, 
         store_kernel<SCONE_QUANT_INT8><<<blocks, 256, 0, stream>>>(rows, table->row_stride, table->num_rows, table->dim, 0, table->scale_offset, d_rows_f32, d_row_ids, row_base, k, nullptr);
     else
         store_kernel<SCONE_QUANT_INT4><<<blocks, 256, 0, stream>>>(rows, table->row_stride, table->num_rows, table->dim, table->group, table->scale_offset, d_rows_f32, d_row_ids, row_base, k, nullptr);
+    SCONE_LAUNCHED();
+    return SCONE_OK;
+}
+
+int scone_embed_mean_forward(const scone_index_t *index, const scone_table_desc_t *table, const int64_t *d_ids, int64_t B, int64_t L,
+                             int32_t *d_work, void *d_out, int32_t out_dtype, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SCONE_REQUIRE(index && table, "scone_embed_mean_forward: NULL index or table");
+    int rc = check_table(table, "scone_embed_mean_forward");
+    if (rc != SCONE_OK) return rc;
+    SCONE_REQUIRE(out_dtype >= SCONE_OUT_BF16 && out_dtype <= SCONE_OUT_FP32, "scone_embed_mean_forward: unknown out_dtype %d", out_dtype);
+    SCONE_REQUIRE(B >= 0 && L >= 0, "scone_embed_mean_forward: negative shape");
+    const int64_t T = B * L;
+    if (T == 0) return SCONE_OK;
+    SCONE_REQUIRE(d_ids && d_work && d_out, "scone_embed_mean_forward: NULL buffer");
+    const scone_index_impl *ix = reinterpret_cast<const scone_index_impl *>(index);
+    SCONE_REQUIRE(ix->n <= table->num_rows, "scone_embed_mean_forward: index has more f-grams than the table has rows");
+    rc = scone_index_match_all(index, d_ids, B, L, d_work, stream_);
+    if (rc != SCONE_OK) return rc;
+    int group_shift = 0;
+    if (table->quant == SCONE_QUANT_INT4)
+        while ((1 << group_shift) < table->group / 8) ++group_shift;
+    const unsigned blocks = (unsigned)((T + 7) / 8);
+    if (table->quant == SCONE_QUANT_FP16) launch_mean<SCONE_QUANT_FP16>(out_dtype, blocks, stream, table, group_shift, d_work, ix->max_n, T, L, d_out);
+    else if (table->quant == SCONE_QUANT_INT8) launch_mean<SCONE_QUANT_INT8>(out_dtype, blocks, stream, table, group_shift, d_work, ix->max_n, T, L, d_out);
+    else launch_mean<SCONE_QUANT_INT4>(out_dtype, blocks, stream, table, group_shift, d_work, ix->max_n, T, L, d_out);
     SCONE_LAUNCHED();
     return SCONE_OK;
 }

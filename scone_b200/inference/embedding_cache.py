@@ -235,6 +235,66 @@ class EmbeddingCache:
         """Sticky device status bits (synchronises): bit 0 = some missed token id was outside the base table."""
         return 0 if self._status is None else int(self._status.item())
 
+    # ---- fixed binary format (SURVEY.md section 8f rank 2) -------------------------------------------------------------
+    _MAGIC = b"SCONEB2\x00"
+
+    def save_binary(self, path: str) -> None:
+        """Header-carrying flat file: 64-byte header, then num_rows x row_stride row bytes, then num_rows presence bytes.
+        Unlike the reference's raw ``np.memmap`` (``embedding_cache.py:84-89``) it can be reloaded (and memory-mapped)."""
+        import struct
+        t = self.table
+        hdr = struct.pack("<8sIIIIQIQ", self._MAGIC, 1, {"fp16": 0, "int8": 1, "int4": 2}[self.quant], self.embedding_dim,
+                          self.group_size, t.row_stride, t.scale_offset, t.num_rows)
+        with open(path, "wb") as f:
+            f.write(hdr.ljust(64, b"\x00"))
+            st = t.storage
+            step = max(1, (256 << 20) // max(1, t.row_stride))
+            for s0 in range(0, t.num_rows, step):
+                f.write(st[s0:s0 + step].cpu().numpy().tobytes())
+            f.write(self._present.cpu().numpy().astype(np.uint8).tobytes())
+
+    @classmethod
+    def load_binary(cls, path: str, n_gram_extractor: NGramExtractor, cache_dir: Optional[str] = None,
+                    use_memory_map: bool = False, **kwargs) -> "EmbeddingCache":
+        import struct
+        with open(path, "rb") as f:
+            raw = f.read(64)
+        magic, ver, q, dim, group, stride, soff, nrows = struct.unpack("<8sIIIIQIQ", raw[:48])
+        if magic != cls._MAGIC or ver != 1:
+            raise ValueError(f"{path}: not a scone_b200 cache file")
+        cache = cls(n_gram_extractor, dim, cache_dir=cache_dir, use_memory_map=use_memory_map,
+                    quant=["fp16", "int8", "int4"][q], group_size=group, **kwargs)
+        t = cache.table
+        if (t.row_stride, t.scale_offset, t.num_rows) != (stride, soff, nrows):
+            raise ValueError("file geometry does not match this vocabulary / build")
+        mm = np.memmap(path, dtype=np.uint8, mode="r", offset=64, shape=(nrows, stride))
+        step = max(1, (256 << 20) // max(1, stride))
+        for s0 in range(0, nrows, step):
+            t.storage[s0:s0 + step].copy_(torch.from_numpy(np.ascontiguousarray(mm[s0:s0 + step])))
+        present = np.fromfile(path, dtype=np.uint8, offset=64 + nrows * stride, count=nrows)
+        cache._present.copy_(torch.from_numpy(present.astype(bool)))
+        return cache
+
+    @classmethod
+    def from_reference_memmap(cls, mmap_path: str, n_gram_extractor: NGramExtractor, embedding_dim: int,
+                              **kwargs) -> "EmbeddingCache":
+        """Import the raw fp32 ``[N, D]`` file the reference's memmap backend writes to ``cache_dir/embeddings.npy``
+        (``embedding_cache.py:76-91``; it has no ``.npy`` header, which is why the reference cannot reload it)."""
+        n = len(n_gram_extractor)
+        rows = np.memmap(mmap_path, dtype=np.float32, mode="r", shape=(n, embedding_dim))
+        cache = cls(n_gram_extractor, embedding_dim, **kwargs)
+        step = max(1, (256 << 20) // (4 * embedding_dim))
+        for s0 in range(0, n, step):
+            blk = torch.from_numpy(np.ascontiguousarray(rows[s0:s0 + step]))
+            cache.cache_embeddings(list(range(s0, s0 + blk.shape[0])), blk, verbose=False)
+        return cache
+
+    def assemble_mean(self, input_ids: torch.Tensor, dtype: torch.dtype = torch.float32) -> torch.Tensor:
+        """The reference engine's own tensor (``engine.py:235-259``): mean of the rows of all f-grams containing each
+        position, zeros where none.  Optional mode; :meth:`lookup` is the Algorithm-2 path."""
+        from ..table import embed_mean_forward
+        return embed_mean_forward(self.n_gram_extractor.device_index(self.device), self.table, input_ids, dtype)
+
     # ---- persistence (reference :183-243) ----------------------------------------------------------------------
     def save(self, path: str) -> None:
         """One ``.npy`` pickle like the reference, but carrying the packed table and its geometry

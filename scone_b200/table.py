@@ -175,3 +175,17 @@ def embed_gather(table: CacheTable, base_emb: torch.Tensor, input_ids: torch.Ten
             L, ids.data_ptr(), fid.data_ptr(), T, out.data_ptr(), _OUT[base_emb.dtype],
             status.data_ptr() if status is not None else None, _stream_ptr(dev)))
     return out
+
+
+def embed_mean_forward(index: FGramIndex, table: CacheTable, input_ids: torch.Tensor, dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """Reference-CODE semantics (``scone/inference/engine.py:235-259``): per position the mean of the rows of all f-grams
+    containing it, zeros where none -- the tensor the reference passes as ``f_gram_embeddings``.  [B, L, D] in ``dtype``."""
+    ids = index._check_ids(input_ids)
+    B, L = ids.shape
+    dev = index.device
+    work = torch.empty((B, L, index.max_n), dtype=torch.int32, device=dev)
+    out = torch.empty((B, L, table.dim), dtype=dtype, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().scone_embed_mean_forward(index.handle, C.byref(table.desc), ids.data_ptr(), B, L, work.data_ptr(),
+                                                        out.data_ptr(), _OUT[dtype], _stream_ptr(dev)))
+    return out

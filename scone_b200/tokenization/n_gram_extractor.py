@@ -182,6 +182,65 @@ class NGramExtractor:
             print(f"Extracted {len(self)} f-grams")
         return self
 
+    def fit_device(self, tokenized_texts: Iterable[Sequence[int]], verbose: bool = True,
+                   device: Optional[torch.device] = None) -> "NGramExtractor":
+        """``fit`` on the GPU: same vocabulary and ids as :meth:`fit` / the reference.
+
+        The corpus is flattened once; for each n the valid windows (never across texts) are de-duplicated with a device
+        sort (``torch.unique(dim=0)``), counted, and tagged with their first occurrence in the reference's enumeration
+        order (text, n, start) by a scatter-min; one stable sort by (-count, first seen) ranks all lengths together,
+        then truncate to ``max_f_grams`` and drop counts below ``min_freq`` (reference :91-94, in that order).
+        """
+        dev = torch.device(device) if device is not None else (torch.device(self.device) if self.device else _default_device())
+        texts = [np.asarray(t, dtype=np.int64).ravel() for t in tokenized_texts]
+        max_n = self.max_n
+        lens_np = np.array([len(t) for t in texts], dtype=np.int64)
+        M = int(lens_np.sum())
+        rows_l, cnt_l, first_l = [], [], []
+        if M:
+            flat = torch.from_numpy(np.concatenate(texts)).to(dev)
+            if bool((flat < 0).any()) or bool((flat > 0x7FFFFFFF).any()):
+                raise ValueError("token ids must be in [0, 2^31)")
+            lens_t = torch.from_numpy(lens_np).to(dev)
+            text_id = torch.repeat_interleave(torch.arange(len(texts), device=dev), lens_t)
+            offs = torch.cumsum(lens_t, 0) - lens_t
+            start = torch.arange(M, device=dev) - offs[text_id]
+            stride = int(max(1, lens_np.max()))
+            big = torch.iinfo(torch.int64).max
+            for n in range(1, max_n + 1):
+                if M < n:
+                    break
+                p = torch.arange(M - n + 1, device=dev)
+                ok = text_id[p] == text_id[p + n - 1]
+                p = p[ok]
+                if p.numel() == 0:
+                    continue
+                keys = torch.stack([flat[p + k] for k in range(n)], dim=1)
+                uniq, inv, cnt = torch.unique(keys, dim=0, return_inverse=True, return_counts=True)
+                seen = (text_id[p] * max_n + (n - 1)) * stride + start[p]
+                first = torch.full((uniq.shape[0],), big, dtype=torch.int64, device=dev).scatter_reduce_(0, inv, seen, "amin")
+                rows = torch.full((uniq.shape[0], max_n), -1, dtype=torch.int64, device=dev)
+                rows[:, :n] = uniq
+                rows_l.append(rows)
+                cnt_l.append(cnt)
+                first_l.append(first)
+        if rows_l:
+            rows, cnt, first = torch.cat(rows_l), torch.cat(cnt_l), torch.cat(first_l)
+            order = torch.argsort(first)
+            order = order[torch.argsort(-cnt[order], stable=True)][: self.max_f_grams]
+            order = order[cnt[order] >= self.min_freq]
+            rows = rows[order]
+            self._tokens = rows.to(torch.int32).cpu().numpy()
+            self._lens = (rows >= 0).sum(dim=1).to(torch.uint8).cpu().numpy()
+        else:
+            self._tokens = np.zeros((0, max_n), dtype=np.int32)
+            self._lens = np.zeros((0,), dtype=np.uint8)
+        self._maps = None
+        self._drop_index()
+        if verbose:
+            print(f"Extracted {len(self)} f-grams")
+        return self
+
     # ---- device index -----------------------------------------------------------------------------
     def device_index(self, device: Optional[torch.device] = None, load_factor: float = 0.25) -> FGramIndex:
         """The GPU hash index of the current vocabulary (built once, cached)."""

@@ -472,3 +472,83 @@ def test_offloaded_tier_zero_copy_and_staged():
         torch.cuda.synchronize()
         assert np.array_equal(fid2.cpu().numpy(), wid) and np.array_equal(ml2.cpu().numpy(), wlen)
         assert np.array_equal(_bits(out2), want)
+
+
+# ---- SURVEY 8f "next" rows -------------------------------------------------------------------------------------------
+
+def test_fit_device_matches_reference_fit():
+    sb, _ = _mods()
+    z = load_golden("fit_small.npz")
+    offs = z["corpus_offs"]
+    corpus = [z["corpus_flat"][offs[i]:offs[i + 1]].tolist() for i in range(len(offs) - 1)]
+    ex = sb.NGramExtractor(int(z["max_n"]), int(z["min_freq"]), int(z["max_f_grams"])).fit_device(corpus, verbose=False)
+    t, l = ex.vocab_arrays()
+    assert np.array_equal(t, z["vocab_tokens"]) and np.array_equal(l, z["vocab_lens"])
+    ex = sb.NGramExtractor(3, 1, 100).fit_device([[1, 2, 3, 4, 1, 2, 3], [2, 3, 4, 5], [1, 2, 9]], verbose=False)
+    assert np.array_equal(ex.vocab_arrays()[0], load_golden("kat0.npz")["vocab_tokens"])
+    assert sb.NGramExtractor(2, 2, 3).fit_device([[7, 8, 7, 8, 9]], verbose=False).f_gram_to_id == {(7,): 0, (8,): 1, (7, 8): 2}
+    rng = np.random.default_rng(12)
+    for _ in range(15):
+        corpus = [rng.integers(0, 15, size=int(rng.integers(0, 40))).tolist() for _ in range(int(rng.integers(1, 9)))]
+        max_n, min_freq, cap = int(rng.integers(1, 6)), int(rng.integers(1, 4)), int(rng.integers(1, 80))
+        a = sb.NGramExtractor(max_n, min_freq, cap).fit_device(corpus, verbose=False)
+        want = po.fit(corpus, max_n, min_freq, cap)
+        assert [a.id_to_f_gram[i] for i in range(len(a))] == want
+
+
+def test_binary_format_and_reference_memmap_import(tmp_path):
+    sb, S = _mods()
+    z = load_golden("cache_small.npz")
+    ex = sb.NGramExtractor.from_arrays(z["vocab_tokens"], z["vocab_lens"])
+    N, D = z["rows"].shape
+    for quant in ("fp16", "int4" if D % 128 == 0 else "int8"):
+        cache = sb.EmbeddingCache(ex, D, quant=quant)
+        cache.cache_embeddings(list(range(0, N, 2)), torch.from_numpy(z["rows"][0::2]), verbose=False)
+        p = str(tmp_path / f"cache_{quant}.bin")
+        cache.save_binary(p)
+        back = sb.EmbeddingCache.load_binary(p, ex)
+        assert back.quant == quant and torch.equal(back.table.storage, cache.table.storage)
+        assert len(back.embeddings) == len(range(0, N, 2)) and 1 not in back.embeddings and 2 in back.embeddings
+        host = sb.EmbeddingCache.load_binary(p, ex, cache_dir=str(tmp_path), use_memory_map=True)
+        assert host.tier == "host" and torch.equal(host.table.storage, cache.table.storage.cpu())
+    # the raw fp32 file the reference's memmap backend leaves behind (embedding_cache.py:84-91)
+    raw = str(tmp_path / "embeddings.npy")
+    mm = np.memmap(raw, dtype=np.float32, mode="w+", shape=(N, D))
+    mm[:] = z["rows"]
+    mm.flush()
+    imp = sb.EmbeddingCache.from_reference_memmap(raw, ex, D)
+    assert torch.equal(imp.get_embeddings(z["pick"].tolist()), torch.from_numpy(z["gathered"]).half().float())
+
+
+def test_reference_code_mean_mode_golden():
+    """engine.py:235-259 re-enacted on the reference objects (golden `assembled`) vs the optional mean mode."""
+    sb, _ = _mods()
+    z = load_golden("cache_small.npz")
+    ex = sb.NGramExtractor.from_arrays(z["vocab_tokens"], z["vocab_lens"])
+    N, D = z["rows"].shape
+    cache = sb.EmbeddingCache(ex, D, quant="fp16")
+    cache.cache_embeddings(list(range(N)), torch.from_numpy(z["rows"]), verbose=False)
+    q = torch.from_numpy(z["query"])[None].to(DEV)
+    got = cache.assemble_mean(q)[0].cpu().numpy()
+    # exact against the oracle's restatement over the rows as stored (fp16), close to the reference's fp32 rows
+    stored = z["rows"].astype(np.float16).astype(np.float32)
+    want = po.assemble_mean(vocab_dict(z["vocab_tokens"], z["vocab_lens"]), int(z["max_n"]), lambda ids: stored[ids],
+                            z["query"].tolist(), D)
+    np.testing.assert_allclose(got, want, rtol=0, atol=2e-9)
+    np.testing.assert_allclose(got, z["assembled"], rtol=0, atol=2e-5)
+    assert np.array_equal(got == 0, z["assembled"] == 0)              # zeros exactly where the reference has none
+    # batched, other formats: against the oracle on dequantised rows
+    from scone_b200.utils import synthetic as S
+    toks, lens = S.make_vocab_numpy(1500, 5, 120, seed=61, min_n=1)
+    rows = S.make_rows_numpy(1500, 256, seed=62)
+    qq = S.make_stream_numpy(toks, lens, 3, 90, 120, seed=63)
+    for quant in ("int8", "int4"):
+        tab = po.OracleTable.from_fp32(rows, quant)
+        ix = _index(toks, lens)
+        t = sb.CacheTable(1500, 256, quant)
+        t.store(torch.from_numpy(rows).to(DEV))
+        g = sb.embed_mean_forward(ix, t, torch.from_numpy(qq).to(DEV)).cpu().numpy()
+        g2i = vocab_dict(toks, lens)
+        for b in range(3):
+            w = po.assemble_mean(g2i, 5, tab.rows_fp32, qq[b].tolist(), 256)
+            np.testing.assert_allclose(g[b], w, rtol=0, atol=1e-8)
