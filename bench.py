@@ -331,10 +331,39 @@ def run_ours(args, w, rank, local_rank, world):
             dt = float(t.item())
         return world * T * args.steps / dt
 
-    e2e_value = time_e2e(False)
-    e2e = {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": T * 8, "d2h_bytes_per_step": T * 5,
-           "note": "ids from pinned host memory; fgram_id + match_len read back to the host every step; the embeddings stay "
-                   "in HBM for the transformer, as with the reference's get_embeddings(ids, device)"}
+    sync_value = time_e2e(False)
+
+    # the throughput form of the same call: scone_b200.HostPipeline double-buffers the batches, so the H2D copy of batch
+    # k+1 and the D2H read of batch k-1 run under batch k's kernel.  Every step still copies its own ids from pinned host
+    # memory and lands its own match result in pinned host memory inside the timed region.
+    def time_pipelined():
+        pipe = sb.HostPipeline(index, table, base, (B, L))
+        for k in range(max(3, args.warmup)):
+            pipe.submit(h_ids[k % N_BATCHES])
+        pipe.flush()
+        barrier()
+        t0 = time.perf_counter()
+        n_done = 0
+        for k in range(args.steps):
+            if pipe.submit(h_ids[k % N_BATCHES]) is not None:
+                n_done += 1
+        n_done += len(pipe.flush())
+        dt = time.perf_counter() - t0
+        barrier()
+        assert n_done == args.steps
+        if world > 1:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return world * T * args.steps / dt
+
+    pipe_value = time_pipelined()
+    e2e = {"value": max(pipe_value, sync_value), "unit": "tokens/s", "h2d_bytes_per_step": T * 8, "d2h_bytes_per_step": T * 5,
+           "mode": "pipelined (scone_b200.HostPipeline, 2 slots)" if pipe_value >= sync_value else "synchronous call per step",
+           "pipelined": pipe_value, "synchronous": sync_value,
+           "note": "ids from pinned host memory; fgram_id + match_len read back to pinned host memory every step; the embeddings "
+                   "stay in HBM for the transformer, as with the reference's get_embeddings(ids, device). `synchronous` = one "
+                   "blocking lookup per step (copy in, kernel, copy out, stream sync)"}
     if args.e2e_embeds_to_host:
         e2e["embeds_to_host"] = {"value": time_e2e(True), "unit": "tokens/s", "d2h_bytes_per_step": T * 5 + T * D * 2}
 

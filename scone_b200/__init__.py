@@ -11,3 +11,4 @@ from .table import CacheTable, embed_forward, embed_gather, embed_mean_forward, 
 from .tokenization.n_gram_extractor import NGramExtractor  # noqa: F401
 from .inference.embedding_cache import EmbeddingCache  # noqa: F401
 from .models.input_embedding import SconeInputEmbedding  # noqa: F401
+from .pipeline import HostPipeline  # noqa: F401

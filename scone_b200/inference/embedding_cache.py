@@ -259,7 +259,7 @@ class EmbeddingCache:
         import struct
         with open(path, "rb") as f:
             raw = f.read(64)
-        magic, ver, q, dim, group, stride, soff, nrows = struct.unpack("<8sIIIIQIQ", raw[:48])
+        magic, ver, q, dim, group, stride, soff, nrows = struct.unpack("<8sIIIIQIQ", raw[:struct.calcsize("<8sIIIIQIQ")])
         if magic != cls._MAGIC or ver != 1:
             raise ValueError(f"{path}: not a scone_b200 cache file")
         cache = cls(n_gram_extractor, dim, cache_dir=cache_dir, use_memory_map=use_memory_map,
@@ -270,7 +270,7 @@ class EmbeddingCache:
         mm = np.memmap(path, dtype=np.uint8, mode="r", offset=64, shape=(nrows, stride))
         step = max(1, (256 << 20) // max(1, stride))
         for s0 in range(0, nrows, step):
-            t.storage[s0:s0 + step].copy_(torch.from_numpy(np.ascontiguousarray(mm[s0:s0 + step])))
+            t.storage[s0:s0 + step].copy_(torch.from_numpy(np.array(mm[s0:s0 + step])))
         present = np.fromfile(path, dtype=np.uint8, offset=64 + nrows * stride, count=nrows)
         cache._present.copy_(torch.from_numpy(present.astype(bool)))
         return cache

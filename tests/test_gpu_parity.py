@@ -552,3 +552,25 @@ def test_reference_code_mean_mode_golden():
         for b in range(3):
             w = po.assemble_mean(g2i, 5, tab.rows_fp32, qq[b].tolist(), 256)
             np.testing.assert_allclose(g[b], w, rtol=0, atol=1e-8)
+
+
+def test_host_pipeline_matches_direct_call():
+    sb, S = _mods()
+    toks, lens = S.make_vocab_numpy(3000, 4, 300, seed=71)
+    ix = _index(toks, lens)
+    t = sb.CacheTable(3000, 256, "int8")
+    t.store(torch.from_numpy(S.make_rows_numpy(3000, 256, seed=72)).to(DEV))
+    base = torch.from_numpy(S.make_rows_numpy(300, 256, seed=73)).to(DEV).to(torch.bfloat16)
+    B, L = 4, 160
+    hb = [torch.from_numpy(S.make_stream_numpy(toks, lens, B, L, 300, seed=80 + k)).pin_memory() for k in range(7)]
+    pipe = sb.HostPipeline(ix, t, base, (B, L))
+    got = []
+    for h in hb:
+        r = pipe.submit(h)
+        if r is not None:
+            got.append((r[0].clone(), r[1].clone(), r[2].clone()))
+    got += [(r[0].clone(), r[1].clone(), r[2].clone()) for r in pipe.flush()]
+    assert len(got) == len(hb)
+    for h, (e, i, l) in zip(hb, got):
+        we, wi, wl = sb.embed_forward(ix, t, base, h.to(DEV))
+        assert torch.equal(e, we) and torch.equal(i.to(DEV), wi) and torch.equal(l.to(DEV), wl)
