@@ -6,10 +6,10 @@ copies of neighbouring batches overlap the kernel.
         done = pipe.submit(h_ids)               # returns the PREVIOUS batch's result (or None for the first)
     last = pipe.flush()
 
-Each result is ``(embeds [B, L, D] on the device, fgram_id int32 [B, L] pinned host, match_len uint8 [B, L] pinned host)``;
-the device embeddings of a slot stay valid until that slot is submitted again (two slots).  Three streams: copy-in,
-compute (the fused kernel), copy-out; events chain them per slot, so batch k+1's H2D and batch k-1's D2H run under
-batch k's kernel.
+Each result is ``(embeds [B, L, D] on the device, fgram_id int32 [B, L] pinned host, match_len uint8 [B, L] pinned host)``
+and stays valid until the next ``submit`` (three slots: two batches in flight, one held by the caller).  Three streams:
+copy-in, compute (the fused kernel), copy-out; events chain them per slot, so batch k+1's H2D and batch k-1's D2H run
+under batch k's kernel.
 """
 
 from __future__ import annotations
@@ -24,7 +24,7 @@ from .table import CacheTable, embed_forward
 
 class HostPipeline:
     def __init__(self, index: FGramIndex, table: CacheTable, base_emb: torch.Tensor, batch_shape: Tuple[int, int],
-                 pos_emb: Optional[torch.Tensor] = None, slots: int = 2):
+                 pos_emb: Optional[torch.Tensor] = None, slots: int = 3):
         B, L = batch_shape
         dev = index.device
         self.index, self.table, self.base, self.pos = index, table, base_emb, pos_emb
@@ -53,9 +53,6 @@ class HostPipeline:
         if not h_ids.is_pinned() or h_ids.dtype != torch.int64:
             raise ValueError("h_ids must be a pinned int64 host tensor")
         slot = self.k % self.n
-        ready = None
-        if len(self.inflight) == self.n:                     # the slot we are about to reuse: hand its result out first
-            ready = self._result(self.inflight.pop(0))
         with torch.cuda.stream(self.s_in):
             self.s_in.wait_event(self.ev_run[slot])          # previous kernel on this slot has consumed d_ids
             self.d_ids[slot].copy_(h_ids, non_blocking=True)
@@ -73,7 +70,10 @@ class HostPipeline:
             self.ev_out[slot].record(self.s_out)
         self.inflight.append(slot)
         self.k += 1
-        return ready
+        # up to n - 1 batches are in flight while we wait for the oldest; its slot is not reused before the submit after next
+        if len(self.inflight) >= max(1, self.n - 1):
+            return self._result(self.inflight.pop(0))
+        return None
 
     def flush(self):
         """Results of everything still in flight, oldest first."""
