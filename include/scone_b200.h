@@ -200,6 +200,26 @@ int scone_embed_forward_sharded(const scone_index_t *index, const scone_table_de
 int scone_host_gather_rows(const void *h_rows, int64_t row_stride, int64_t num_rows, const int32_t *h_row_ids,
                            int64_t k, void *h_staging, int32_t nthreads);
 
+/* ---- host-fed pipeline ----------------------------------------------------------------------------------
+ * The throughput form of scone_embed_forward for callers whose ids live in HOST memory (the reference's engine
+ * tokenises on the host, scone/inference/engine.py:222-233): `slots` batches rotate through three streams owned by
+ * the pipeline -- copy-in (pinned host ids -> HBM), compute (the fused kernel), copy-out (match result -> pinned
+ * host) -- chained per slot with events, so batch k+1's H2D and batch k-1's D2H run under batch k's kernel.
+ * All buffers are the caller's: per slot d_ids int64 [B*L], d_out [B*L*D] out_dtype, d_meta / h_meta 5*B*L bytes
+ * (fgram_id int32 [B*L] followed by match_len uint8 [B*L]; h_meta pinned).  The embeddings stay on the device. */
+typedef struct scone_pipeline scone_pipeline_t;
+int scone_pipeline_create(const scone_index_t *index, const scone_table_desc_t *table, const void *d_base_emb,
+                          int64_t base_rows, const void *d_pos_emb, int64_t B, int64_t L, int32_t out_dtype,
+                          int32_t slots, void *const *d_ids_slots, void *const *d_out_slots, void *const *d_meta_slots,
+                          void *const *h_meta_slots, uint32_t *d_status, scone_pipeline_t **out);
+/* Enqueue one batch from pinned host ids; *slot receives the slot it went to.  If that slot's previous batch has not
+ * been waited for yet, the call waits for it first.  Returns without waiting for the new batch. */
+int scone_pipeline_submit(scone_pipeline_t *p, const int64_t *h_ids_pinned, int32_t *slot);
+/* Block the calling host thread until the batch in `slot` is complete: its embeddings are in d_out_slots[slot] and
+ * its match result in h_meta_slots[slot]. */
+int scone_pipeline_wait(scone_pipeline_t *p, int32_t slot);
+int scone_pipeline_destroy(scone_pipeline_t *p);
+
 /* Number of kernels this library has launched from the calling process (monotonic). */
 int64_t scone_launch_count(void);
 

@@ -16,7 +16,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB_DIR = os.path.join(PKG, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libscone_b200.so")
-SOURCES = ["api.cu", "index.cu", "table.cu", "embed.cu"]
+SOURCES = ["api.cu", "index.cu", "table.cu", "embed.cu", "pipeline.cu"]
 HEADERS = ["common.cuh", "match.cuh", os.path.join("..", "..", "include", "scone_b200.h")]
 
 NVCC_FLAGS = [

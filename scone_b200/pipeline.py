@@ -1,25 +1,28 @@
-"""Host-fed lookups, double-buffered: ids arrive in pinned HOST memory, match results go back to the host, and the
-copies of neighbouring batches overlap the kernel.
+"""Host-fed lookups, multi-buffered: ids arrive in pinned HOST memory, match results go back to the host, and the
+copies of neighbouring batches overlap the kernel.  Thin wrapper over the native ``scone_pipeline_*`` runtime
+(``csrc/pipeline.cu``: three streams, per-slot events, ``cudaMemcpyAsync`` in and out around the fused kernel).
 
-    pipe = HostPipeline(cache_or_parts, batch_shape=(B, L))
+    pipe = HostPipeline(index, table, base_emb, batch_shape=(B, L))
     for h_ids in batches:                       # pinned int64 [B, L] tensors
-        done = pipe.submit(h_ids)               # returns the PREVIOUS batch's result (or None for the first)
-    last = pipe.flush()
+        done = pipe.submit(h_ids)               # the oldest finished batch, or None while the pipeline fills
+    rest = pipe.flush()
 
 Each result is ``(embeds [B, L, D] on the device, fgram_id int32 [B, L] pinned host, match_len uint8 [B, L] pinned host)``
-and stays valid until the next ``submit`` (three slots: two batches in flight, one held by the caller).  Three streams:
-copy-in, compute (the fused kernel), copy-out; events chain them per slot, so batch k+1's H2D and batch k-1's D2H run
-under batch k's kernel.
+and stays valid until the next ``submit`` (three slots: two batches in flight, one held by the caller).  To consume the
+embeddings on another stream, call ``torch.cuda.current_stream().synchronize()``-free code after ``submit`` returned them:
+the batch is complete (its copy-out, which follows the kernel, has been waited for).
 """
 
 from __future__ import annotations
 
+import ctypes as C
 from typing import Optional, Tuple
 
 import torch
 
+from . import _lib
 from .index import FGramIndex
-from .table import CacheTable, embed_forward
+from .table import _OUT, CacheTable
 
 
 class HostPipeline:
@@ -27,50 +30,39 @@ class HostPipeline:
                  pos_emb: Optional[torch.Tensor] = None, slots: int = 3):
         B, L = batch_shape
         dev = index.device
+        if base_emb.dtype not in (torch.bfloat16, torch.float16) or base_emb.device != dev or not base_emb.is_contiguous():
+            raise ValueError("base_emb must be a contiguous bf16/fp16 tensor on the index device")
         self.index, self.table, self.base, self.pos = index, table, base_emb, pos_emb
-        self.n = slots
-        self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(device=dev) for _ in range(3))
-        mk = lambda *shape, dtype: torch.empty(shape, dtype=dtype, device=dev)
-        self.d_ids = [mk(B, L, dtype=torch.int64) for _ in range(slots)]
-        self.out = [mk(B, L, table.dim, dtype=base_emb.dtype) for _ in range(slots)]
-        self.d_id = [mk(B, L, dtype=torch.int32) for _ in range(slots)]
-        self.d_len = [mk(B, L, dtype=torch.uint8) for _ in range(slots)]
-        self.h_id = [torch.empty((B, L), dtype=torch.int32).pin_memory() for _ in range(slots)]
-        self.h_len = [torch.empty((B, L), dtype=torch.uint8).pin_memory() for _ in range(slots)]
+        self.B, self.L, self.n = B, L, slots
+        T = B * L
+        self.d_ids = [torch.empty((B, L), dtype=torch.int64, device=dev) for _ in range(slots)]
+        self.out = [torch.empty((B, L, table.dim), dtype=base_emb.dtype, device=dev) for _ in range(slots)]
+        self.d_meta = [torch.empty((5 * T,), dtype=torch.uint8, device=dev) for _ in range(slots)]
+        self.h_meta = [torch.empty((5 * T,), dtype=torch.uint8).pin_memory() for _ in range(slots)]
+        self.h_id = [m[:4 * T].view(torch.int32).view(B, L) for m in self.h_meta]
+        self.h_len = [m[4 * T:].view(B, L) for m in self.h_meta]
         self.status = torch.zeros((1,), dtype=torch.int32, device=dev)
-        self.ev_in = [torch.cuda.Event() for _ in range(slots)]
-        self.ev_run = [torch.cuda.Event() for _ in range(slots)]
-        self.ev_out = [torch.cuda.Event() for _ in range(slots)]
-        self.k = 0
+        arr = lambda ts: (C.c_void_p * slots)(*[t.data_ptr() for t in ts])
+        self._h = C.c_void_p()
+        torch.cuda.synchronize(dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().scone_pipeline_create(
+                index.handle, C.byref(table.desc), base_emb.data_ptr(), base_emb.shape[0],
+                pos_emb.data_ptr() if pos_emb is not None else None, B, L, _OUT[base_emb.dtype], slots,
+                arr(self.d_ids), arr(self.out), arr(self.d_meta), arr(self.h_meta), self.status.data_ptr(), C.byref(self._h)))
         self.inflight = []
+        self._slot = C.c_int32()
 
-    def _result(self, slot):
-        self.ev_out[slot].synchronize()
+    def _result(self, slot: int):
+        _lib.check(_lib.load().scone_pipeline_wait(self._h, slot))
         return self.out[slot], self.h_id[slot], self.h_len[slot]
 
     def submit(self, h_ids: torch.Tensor):
-        """Enqueue one batch (pinned int64 [B, L]); returns the oldest finished result once the pipeline is full."""
-        if not h_ids.is_pinned() or h_ids.dtype != torch.int64:
-            raise ValueError("h_ids must be a pinned int64 host tensor")
-        slot = self.k % self.n
-        with torch.cuda.stream(self.s_in):
-            self.s_in.wait_event(self.ev_run[slot])          # previous kernel on this slot has consumed d_ids
-            self.d_ids[slot].copy_(h_ids, non_blocking=True)
-            self.ev_in[slot].record(self.s_in)
-        with torch.cuda.stream(self.s_run):
-            self.s_run.wait_event(self.ev_in[slot])
-            self.s_run.wait_event(self.ev_out[slot])         # previous results of this slot have left the device
-            embed_forward(self.index, self.table, self.base, self.d_ids[slot], pos_emb=self.pos, out=self.out[slot],
-                          status=self.status, out_id=self.d_id[slot], out_len=self.d_len[slot])
-            self.ev_run[slot].record(self.s_run)
-        with torch.cuda.stream(self.s_out):
-            self.s_out.wait_event(self.ev_run[slot])
-            self.h_id[slot].copy_(self.d_id[slot], non_blocking=True)
-            self.h_len[slot].copy_(self.d_len[slot], non_blocking=True)
-            self.ev_out[slot].record(self.s_out)
-        self.inflight.append(slot)
-        self.k += 1
-        # up to n - 1 batches are in flight while we wait for the oldest; its slot is not reused before the submit after next
+        """Enqueue one batch (pinned int64 [B, L]); returns the oldest finished result once two batches are in flight."""
+        if not h_ids.is_pinned() or h_ids.dtype != torch.int64 or h_ids.numel() != self.B * self.L or not h_ids.is_contiguous():
+            raise ValueError("h_ids must be a contiguous pinned int64 host tensor of the pipeline's batch shape")
+        _lib.check(_lib.load().scone_pipeline_submit(self._h, h_ids.data_ptr(), C.byref(self._slot)))
+        self.inflight.append(int(self._slot.value))
         if len(self.inflight) >= max(1, self.n - 1):
             return self._result(self.inflight.pop(0))
         return None
@@ -80,3 +72,14 @@ class HostPipeline:
         res = [self._result(s) for s in self.inflight]
         self.inflight = []
         return res
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            _lib.load().scone_pipeline_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
