@@ -43,6 +43,9 @@ WORKLOADS = {
     # N here is PER GPU (12.5 M rows x 8 192 B = 102 GB per GPU; 100 M f-grams at 8 GPUs)
     "config4": dict(N=12_500_000, D=4096, V=128_000, max_n=5, quant="fp16", B=256, L=2048, tier="sharded",
                     desc="hidden 4096, 100M f-grams (12.5M per GPU), FP16 cache row-sharded by id % W via NCCL all-to-all, batch 256x2048 per GPU"),
+    # config 3's table row-sharded instead of replicated ("8-GPU run: replicas and sharded variant for comparison")
+    "config3s": dict(N=1_250_000, D=4096, V=128_000, max_n=5, quant="int4", B=256, L=2048, tier="sharded",
+                     desc="hidden 4096, 10M f-grams (1.25M per GPU), INT4 g128 cache row-sharded by id % W, batch 256x2048 per GPU"),
     # N is capped by the box's host RAM (pinned); 200 M rows need 416 GB
     "config5": dict(N=200_000_000, D=2048, V=128_000, max_n=5, quant="int8", B=256, L=2048, tier="host",
                     desc="hidden 2048, 200M f-grams, INT8 cache in pinned host RAM read zero-copy (TMA bulk over the host link), batch 256x2048"),
