@@ -99,7 +99,10 @@ __host__ __device__ __forceinline__ uint64_t hash_finish(uint64_t h, int n) {
 
 #ifdef __CUDACC__
 
-__device__ __forceinline__ uint64_t home_slot(uint64_t h, uint64_t cap) { return __umul64hi(h, cap); }
+// Home slots are EVEN: a probe step reads the aligned pair (s, s+1) = one 64-byte block, which is what a DRAM access
+// fetches anyway, so checking two slots per dependent step is free in traffic and halves the probe chain.
+// (capacity is a multiple of 4.)
+__device__ __forceinline__ uint64_t home_slot(uint64_t h, uint64_t cap) { return __umul64hi(h, cap >> 1) << 1; }
 
 // 256-bit slot load (LDG.E.256); slots are read-only while any lookup runs.
 __device__ __forceinline__ void load_slot(const Slot *p, int32_t (&w)[8]) {
@@ -111,16 +114,23 @@ __device__ __forceinline__ void load_slot(const Slot *p, int32_t (&w)[8]) {
 
 // key[0..6]: reversed tokens, -1 padded.  Returns the f-gram id or -1.
 __device__ __forceinline__ int32_t probe(const IndexView &ix, uint64_t h, const int32_t (&key)[7]) {
-    uint64_t s = home_slot(h, ix.cap);
-    for (uint64_t it = 0; it < ix.cap; ++it) {
-        int32_t w[8];
-        load_slot(ix.slots + s, w);
-        if (w[0] < 0) return -1;
+    uint64_t s = home_slot(h, ix.cap);  // even; the insert order is s, s+1, s+2, ... so scanning pairs in order is exact
+    for (uint64_t it = 0; it < ix.cap; it += 2) {
+        int32_t a[8], b[8];
+        load_slot(ix.slots + s, a);
+        load_slot(ix.slots + s + 1, b);
+        if (a[0] < 0) return -1;
         bool eq = true;
 #pragma unroll
-        for (int k = 0; k < 7; ++k) eq &= (w[k + 1] == key[k]);
-        if (eq) return w[0];
-        if (++s == ix.cap) s = 0;
+        for (int k = 0; k < 7; ++k) eq &= (a[k + 1] == key[k]);
+        if (eq) return a[0];
+        if (b[0] < 0) return -1;
+        eq = true;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) eq &= (b[k + 1] == key[k]);
+        if (eq) return b[0];
+        s += 2;
+        if (s == ix.cap) s = 0;
     }
     return -1;
 }
