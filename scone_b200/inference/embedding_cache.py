@@ -70,6 +70,9 @@ class EmbeddingCache:
         device: Optional[torch.device] = None,
         tier: Optional[str] = None,
     ) -> None:
+        """``quant``: "fp16" | "int8" | "int4" (``group_size`` for int4); ``tier``: "hbm" (default), "host" (pinned host
+        memory, also selected by ``use_memory_map=True``) or "sharded" (rows split by id % world over the default
+        process group and read over NVLink; needs ``torch.distributed`` initialised with NCCL)."""
         self.n_gram_extractor = n_gram_extractor
         self.embedding_dim = embedding_dim
         self.cache_dir = cache_dir
@@ -84,6 +87,9 @@ class EmbeddingCache:
         self._base_emb: Optional[torch.Tensor] = None
         self._pos_emb: Optional[torch.Tensor] = None
         self._status: Optional[torch.Tensor] = None
+        self._sharded = None
+        if self.tier not in ("hbm", "host", "sharded"):
+            raise ValueError("tier must be 'hbm', 'host' or 'sharded'")
         if self.cache_dir is not None and not os.path.exists(self.cache_dir):
             os.makedirs(self.cache_dir)
 
@@ -104,7 +110,13 @@ class EmbeddingCache:
             if self.use_memory_map and self.cache_dir is None:
                 raise ValueError("Cache directory must be provided for memory mapping")     # reference :72-73
             n = len(self.n_gram_extractor)
-            self._table = CacheTable(n, self.embedding_dim, self.quant, self.group_size, self.device, self.tier)
+            if self.tier == "sharded":
+                # rows split by id % world over the default process group, shards mapped by every rank (NVLink)
+                from ..sharded import PeerShardedTable
+                self._sharded = PeerShardedTable(n, self.embedding_dim, self.quant, self.group_size, self.device)
+                self._table = self._sharded.local
+            else:
+                self._table = CacheTable(n, self.embedding_dim, self.quant, self.group_size, self.device, self.tier)
             self._present = torch.zeros((n,), dtype=torch.bool, device=self.device)
         return self._table
 
@@ -147,8 +159,13 @@ class EmbeddingCache:
             raise ValueError(f"embeddings must be [{len(ids)}, {self.embedding_dim}]")
         table = self.table
         id_t = torch.tensor(ids, dtype=torch.int64, device=self.device)
-        if len(ids) and (int(id_t.min()) < 0 or int(id_t.max()) >= table.num_rows):
+        if len(ids) and (int(id_t.min()) < 0 or int(id_t.max()) >= len(self.n_gram_extractor)):
             raise IndexError("f-gram id out of range")                                     # memmap backend: IndexError
+        if self.tier == "sharded":
+            # every rank may be handed every row; each keeps the ones it owns.  Call publish() after the last store.
+            self._sharded.store_owned(embeddings.to(torch.float32), id_t)
+            self._present[id_t] = True
+            return
         chunk = max(1, (256 << 20) // (4 * self.embedding_dim))
         for s in range(0, len(ids), chunk):
             rows = embeddings[s:s + chunk].to(device=self.device, dtype=torch.float32, non_blocking=True)
@@ -228,8 +245,19 @@ class EmbeddingCache:
         index = self.n_gram_extractor.device_index(self.device)
         if self._status is None:
             self._status = torch.zeros((1,), dtype=torch.int32, device=self.device)
+        if self.tier == "sharded":
+            from ..sharded import embed_forward_sharded
+            self.table
+            return embed_forward_sharded(index, self._sharded, self._base_emb, input_ids,
+                                         self._pos_emb if add_positions else None, out, self._status)
         return embed_forward(index, self.table, self._base_emb, input_ids, self._pos_emb if add_positions else None, out,
                              self._status)
+
+    def publish(self) -> None:
+        """Sharded tier: make this rank's rows visible to its peers (collective; call once after the last store)."""
+        if self.tier == "sharded":
+            self.table
+            self._sharded.publish()
 
     def status(self) -> int:
         """Sticky device status bits (synchronises): bit 0 = some missed token id was outside the base table."""

@@ -61,6 +61,18 @@ for quant, D, max_n in (("int4", 4096, 5), ("fp16", 1024, 3), ("int8", 2048, 4))
         and int(status.item()) == 0
     print(f"rank {rank}/{world} {quant} D={D} peer-direct: {'OK' if good2 else 'MISMATCH'}", flush=True)
     ok = ok and good2
+# the drop-in class with tier="sharded": every rank offers all rows, keeps its own, looks up through peer memory
+ex = sb.NGramExtractor.from_arrays(toks, lens)
+cache = sb.EmbeddingCache(ex, D, quant=quant, out_dtype=torch.bfloat16, device=dev, tier="sharded")
+cache.cache_embeddings(list(range(N)), torch.from_numpy(rows), verbose=False)
+cache.publish()
+cache.set_base_embedding(base)
+emb3, fid3, _ = cache.lookup(torch.from_numpy(q).to(dev))
+torch.cuda.synchronize()
+dist.barrier()
+good3 = np.array_equal(emb3.view(torch.int16).cpu().numpy().view(np.uint16), want) and np.array_equal(fid3.cpu().numpy(), wid)
+print(f"rank {rank}/{world} EmbeddingCache(tier='sharded'): {'OK' if good3 else 'MISMATCH'}", flush=True)
+ok = ok and good3
 flag = torch.tensor([0 if ok else 1], device=dev)
 dist.all_reduce(flag)
 dist.destroy_process_group()

@@ -574,3 +574,53 @@ def test_host_pipeline_matches_direct_call():
     for h, (e, i, l) in zip(hb, got):
         we, wi, wl = sb.embed_forward(ix, t, base, h.to(DEV))
         assert torch.equal(e, we) and torch.equal(i.to(DEV), wi) and torch.equal(l.to(DEV), wl)
+
+
+def test_hypothesis_gpu_lookup_vs_oracle():
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.data())
+    def run(data):
+        max_n = data.draw(st.integers(1, 7))
+        V = data.draw(st.integers(1, 10))
+        grams = data.draw(st.lists(st.lists(st.integers(0, V - 1), min_size=1, max_size=max_n).map(tuple), max_size=60, unique=True))
+        B = data.draw(st.integers(1, 3))
+        L = data.draw(st.integers(1, 70))
+        q = np.array(data.draw(st.lists(st.lists(st.integers(0, V), min_size=L, max_size=L), min_size=B, max_size=B)), dtype=np.int64)
+        toks = np.full((len(grams), max_n), -1, np.int32)
+        lens = np.zeros(len(grams), np.uint8)
+        for i, g in enumerate(grams):
+            toks[i, :len(g)] = g
+            lens[i] = len(g)
+        ix = _index(toks, lens, load_factor=data.draw(st.sampled_from([0.1, 0.25, 0.5, 0.9])))
+        fid, ml = ix.lookup(torch.from_numpy(q).to(DEV))
+        wid, wl = po.match_batch({g: i for i, g in enumerate(grams)}, max_n, q)
+        assert np.array_equal(fid.cpu().numpy(), wid) and np.array_equal(ml.cpu().numpy(), wl)
+        ix.close()
+
+    run()
+
+
+@pytest.mark.parametrize("quant,D,max_n", [("fp16", 8192, 5), ("int8", 16384, 3), ("int4", 16384, 2), ("fp16", 4096, 1)])
+def test_embed_forward_rows_too_wide_for_the_ring(quant, D, max_n):
+    """Rows that do not fit the shared-memory ring take the register-load variant of the kernel."""
+    _embed_case(quant, "bf16", D, max_n, N=100 if max_n == 1 else 600, V=300, B=2, L=75, seed=D + max_n, min_n=1 if max_n < 3 else 2)
+
+
+def test_embed_forward_all_hits_and_all_misses():
+    sb, S = _mods()
+    toks = np.array([[5, -1], [5, 5]], np.int32)
+    lens = np.array([1, 2], np.uint8)
+    ix = _index(toks, lens)
+    t = sb.CacheTable(2, 256, "int8")
+    rows = S.make_rows_numpy(2, 256, seed=1)
+    t.store(torch.from_numpy(rows).to(DEV))
+    base = torch.from_numpy(S.make_rows_numpy(10, 256, seed=2)).to(DEV).to(torch.bfloat16)
+    allhit = torch.full((3, 40), 5, dtype=torch.long, device=DEV)
+    out, fid, ml = sb.embed_forward(ix, t, base, allhit)
+    assert fid[:, 0].tolist() == [0, 0, 0] and bool((fid[:, 1:] == 1).all()) and bool((ml[:, 1:] == 2).all())
+    assert torch.equal(out[:, 1:], t.gather(torch.tensor([1], device=DEV), torch.bfloat16).expand(3, 39, 256))
+    allmiss = torch.full((3, 40), 7, dtype=torch.long, device=DEV)
+    out, fid, ml = sb.embed_forward(ix, t, base, allmiss)
+    assert bool((fid == -1).all()) and bool((ml == 0).all()) and torch.equal(out, base[7].expand(3, 40, 256))

@@ -221,3 +221,57 @@ def test_embed_forward_py_vs_c(quant, out_dtype):
     assert err == 0
     assert np.array_equal(cid, fid) and np.array_equal(clen, ml)
     assert np.array_equal(cout, out)
+
+
+# ---- property-based fuzz (hypothesis over vocabularies / sequences / max_n) --------------------------
+
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.data())
+def test_hypothesis_match_py_window_vs_direct_vs_c(data):
+    max_n = data.draw(st.integers(1, 7))
+    V = data.draw(st.integers(1, 12))
+    grams = data.draw(st.lists(st.lists(st.integers(0, V - 1), min_size=1, max_size=max_n).map(tuple), max_size=40, unique=True))
+    rows = data.draw(st.lists(st.lists(st.integers(0, V), min_size=1, max_size=30), min_size=1, max_size=4))
+    L = max(len(r) for r in rows)
+    q = np.array([r + [V] * (L - len(r)) for r in rows], dtype=np.int64)      # V = a token outside the vocabulary as pad
+    g2i = {g: i for i, g in enumerate(grams)}
+    toks = np.full((len(grams), max_n), -1, np.int32)
+    lens = np.zeros(len(grams), np.uint8)
+    for i, g in enumerate(grams):
+        toks[i, :len(g)] = g
+        lens[i] = len(g)
+    a = po.match_batch(g2i, max_n, q, via_window=True)
+    b = po.match_batch(g2i, max_n, q, via_window=False)
+    c = COracleIndex(toks, lens).match(q, nthreads=2)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert np.array_equal(a[0], c[0]) and np.array_equal(a[1], c[1])
+    # a match is a real f-gram ending there, and nothing longer in the vocabulary ends there
+    for bi in range(q.shape[0]):
+        for i in range(L):
+            n = int(a[1][bi, i])
+            if n:
+                assert g2i[tuple(q[bi, i - n + 1:i + 1].tolist())] == a[0][bi, i]
+            for m in range(n + 1, min(max_n, i + 1) + 1):
+                assert tuple(q[bi, i - m + 1:i + 1].tolist()) not in g2i
+
+
+@settings(max_examples=40, deadline=None)
+@given(st.integers(0, 2 ** 32 - 1), st.sampled_from(["fp16", "int8", "int4"]), st.sampled_from(["bf16", "fp16"]))
+def test_hypothesis_dequant_py_vs_c(seed, quant, out_dtype):
+    from scone_b200.utils.synthetic import pack_table_numpy
+    rng = np.random.default_rng(seed)
+    D = 128 * int(rng.integers(1, 4))
+    rows = (rng.standard_normal((5, D)) * float(10.0 ** rng.uniform(-6, 3))).astype(np.float32)
+    rows[int(rng.integers(0, 5))] = 0
+    tab = po.OracleTable.from_fp32(rows, quant)
+    packed, stride, soff = pack_table_numpy(quant, tab.payload, tab.scales)
+    toks = np.arange(5, dtype=np.int32).reshape(5, 1)
+    cix = COracleIndex(toks, np.ones(5, np.uint8))
+    base = np.zeros((6, D), np.uint16)
+    q = np.arange(6, dtype=np.int64).reshape(1, 6)
+    out, fid, _, err = cix.embed(quant, D, 128, packed, stride, packed[:, soff:] if soff else None, stride, base, q, out_dtype)
+    assert err == 0 and fid.tolist() == [[0, 1, 2, 3, 4, -1]]
+    assert np.array_equal(out[0, :5], po.cast_bits(tab.rows_fp32(np.arange(5)), out_dtype))
