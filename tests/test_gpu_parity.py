@@ -605,7 +605,7 @@ def test_hypothesis_gpu_lookup_vs_oracle():
 @pytest.mark.parametrize("quant,D,max_n", [("fp16", 8192, 5), ("int8", 16384, 3), ("int4", 16384, 2), ("fp16", 4096, 1)])
 def test_embed_forward_rows_too_wide_for_the_ring(quant, D, max_n):
     """Rows that do not fit the shared-memory ring take the register-load variant of the kernel."""
-    _embed_case(quant, "bf16", D, max_n, N=100 if max_n == 1 else 600, V=300, B=2, L=75, seed=D + max_n, min_n=1 if max_n < 3 else 2)
+    _embed_case(quant, "bf16", D, max_n, N=60 if max_n == 1 else 600, V=300, B=2, L=75, seed=D + max_n, min_n=1 if max_n < 3 else 2)
 
 
 def test_embed_forward_all_hits_and_all_misses():
