@@ -105,3 +105,31 @@ def test_synthetic_generators():
     assert qd.shape == (2, 64) and qd.dtype == torch.int64
     fid, _ = po.match_batch(vocab_dict(td.numpy(), ld.numpy()), 4, qd.numpy())
     assert (fid >= 0).mean() > 0.7
+
+
+def test_tiers_and_pipeline_refuse_cpu():
+    """No CPU path anywhere: the tier / pipeline wrappers raise before touching the library when there is no CUDA tensor."""
+    import torch
+    import scone_b200 as sb
+    from scone_b200 import sharded
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    with pytest.raises((ValueError, RuntimeError)):
+        sb.CacheTable(4, 64, "int8")
+    with pytest.raises(ValueError):
+        sb.EmbeddingCache(sb.NGramExtractor.from_arrays(np.array([[1, 2]], np.int32), np.array([2], np.uint8)), 64, tier="nvme")
+    assert sharded.shard_rows(10, 3, 4) == 2 and sharded.shard_rows(2, 3, 4) == 0
+
+
+def test_header_cites_reference_for_every_entry_point():
+    """include/scone_b200.h must say which reference code each compute entry point replaces (file:line)."""
+    header = open(os.path.join(ROOT, "include", "scone_b200.h")).read()
+    for needle in ("n_gram_extractor.py:121-122", "embedding_cache.py:173", "embedding_cache.py:113-147", "embedding_cache.py:56-111",
+                   "engine.py:235-266", "language_model.py:239", "engine.py:235-259", "n_gram_extractor.py:106-126"):
+        assert needle in header, needle
+    integration = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    from scone_b200 import _lib
+    for sym in _lib.SYMBOLS:
+        if sym.startswith(("scone_index", "scone_table", "scone_embed", "scone_pipeline", "scone_host")):
+            stem = sym if sym in integration else sym.rsplit("_", 1)[0]
+            assert stem in integration, sym

@@ -76,7 +76,14 @@ def main():
     nbytes = int(bpt * T)
     a = torch.empty(nbytes // 2, dtype=torch.uint8, device=dev)
     b = torch.empty_like(a)
-    report("torch_copy_same_bytes", graph_time(lambda k: b.copy_(a)))
+    report("torch_copy_same_bytes(uint8)", graph_time(lambda k: b.copy_(a)))
+    a4, b4 = a[: (nbytes // 2) // 16 * 16].view(torch.float32), b[: (nbytes // 2) // 16 * 16].view(torch.float32)
+    report("torch_copy_same_bytes(float32, vectorised)", graph_time(lambda k: b4.copy_(a4)))
+    big_a = torch.empty(1 << 30, dtype=torch.bfloat16, device=dev)
+    big_b = torch.empty_like(big_a)
+    ms = graph_time(lambda k: big_b.copy_(big_a), steps=3, reps=3)
+    print(json.dumps({"variant": "torch_copy_4GiB_traffic(bf16)", "us": ms * 1e3, "GBs": 2 * big_a.numel() * 2 / (ms * 1e-3) / 1e9}), flush=True)
+    del big_a, big_b
     report("lookup_only", graph_time(lambda k: index.lookup(batches[k % 8])))
     fid, _ = index.lookup(batches[0])
     fids = [index.lookup(batches[k])[0] for k in range(8)]
