@@ -279,9 +279,13 @@ def run_ours(args, w, rank, local_rank, world):
         graph.replay()                       # one untimed replay (graph upload)
         stream.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        graph.replay()
+        e1.record(stream)
+        stream.synchronize()
+        reps = max(1, min(400, int(0.4 / max(1e-5, e0.elapsed_time(e1) * 1e-3))))   # keep the GPU busy ~0.4 s either side for the clock samples
         barrier()
         with ClockSampler(local_rank) as clocks:
-            reps = max(1, int(0.6 / max(1e-4, args.steps * 4e-5)))      # keep the GPU busy >= ~0.6 s for the clock samples
             for _ in range(reps):
                 graph.replay()
             stream.synchronize()
