@@ -203,10 +203,11 @@ __global__ void __launch_bounds__(32 * (NM + NG), MINB) embed_kernel(const Embed
     if (warp < NM) {
         // ===== matcher warps: resolve the CTA's tiles round-robin, running ahead of the gather warps =====
         const int j = lane / P;
+        const int back = p.ix.max_n - 1;
         int64_t it = warp;
         int64_t tile = blockIdx.x + it * gridDim.x;
         int32_t wtok = -1;
-        if (!p.fgram_in && tile < p.num_tiles) wtok = load_window_token<P>(p.ids, p.T, tile * G, lane);
+        if (!p.fgram_in && tile < p.num_tiles) wtok = load_window_token<P>(p.ids, p.T, tile * G, lane, back);
         for (; tile < p.num_tiles; it += NM, tile += (int64_t)NM * gridDim.x) {
             const int q = (int)(it % R);
             const int64_t base = tile * G;
@@ -225,10 +226,10 @@ __global__ void __launch_bounds__(32 * (NM + NG), MINB) embed_kernel(const Embed
                     }
                 }
             } else {
-                if (ntile < p.num_tiles) ntok = load_window_token<P>(p.ids, p.T, ntile * G, lane);
-                const WindowMatch m = match_window<P>(p.ix, wtok, p.T, p.L, base, lane);
+                if (ntile < p.num_tiles) ntok = load_window_token<P>(p.ids, p.T, ntile * G, lane, back);
+                const WindowMatch m = match_window<P>(p.ix, wtok, p.T, p.L, base, lane, back);
                 fid = m.fid;
-                tok = own_token<P>(wtok, lane);
+                tok = own_token<P>(wtok, lane, back);
                 if ((int64_t)tok >= p.V) tok = -1;
                 if ((lane % P) == 0 && i < p.T) {
                     if (p.out_id) p.out_id[i] = m.fid;
@@ -379,11 +380,12 @@ __global__ void __launch_bounds__(32 * (NM + NG), MINB) embed_bulk_kernel(const 
 
     if (warp < NM) {
         const int j = lane / P;
+        const int back = p.ix.max_n - 1;
         const uint64_t pol = policy_evict_first();
         int64_t it = warp;
         int64_t tile = blockIdx.x + it * gridDim.x;
         int32_t wtok = -1;
-        if (!p.fgram_in && tile < p.num_tiles) wtok = load_window_token<P>(p.ids, p.T, tile * G, lane);
+        if (!p.fgram_in && tile < p.num_tiles) wtok = load_window_token<P>(p.ids, p.T, tile * G, lane, back);
         for (; tile < p.num_tiles; it += NM, tile += (int64_t)NM * gridDim.x) {
             const int q = (int)(it % R);
             const int64_t base = tile * G;
@@ -401,10 +403,10 @@ __global__ void __launch_bounds__(32 * (NM + NG), MINB) embed_bulk_kernel(const 
                     }
                 }
             } else {
-                if (ntile < p.num_tiles) ntok = load_window_token<P>(p.ids, p.T, ntile * G, lane);
-                const WindowMatch m = match_window<P>(p.ix, wtok, p.T, p.L, base, lane);
+                if (ntile < p.num_tiles) ntok = load_window_token<P>(p.ids, p.T, ntile * G, lane, back);
+                const WindowMatch m = match_window<P>(p.ix, wtok, p.T, p.L, base, lane, back);
                 fid = m.fid;
-                tok = own_token<P>(wtok, lane);
+                tok = own_token<P>(wtok, lane, back);
                 if ((int64_t)tok >= p.V) tok = -1;
                 if ((lane % P) == 0 && i < p.T) {
                     if (p.out_id) p.out_id[i] = m.fid;
@@ -462,7 +464,6 @@ __global__ void __launch_bounds__(32 * (NM + NG), MINB) embed_bulk_kernel(const 
     }
 }
 
-static int lanes_per_token(int max_n) { return max_n <= 1 ? 1 : max_n <= 2 ? 2 : max_n <= 4 ? 4 : 8; }
 
 static int num_sms() {
     static int n = 0;
@@ -515,15 +516,15 @@ static int launch_ldg(EmbedParams &p, cudaStream_t stream) {
 }
 
 // Ring geometry for the bulk variant; returns false when rows are too wide for the budget.
-// The ring is a multiple of the matcher count so that every slot is only ever filled by one matcher (mbarrier
-// parity waits are then never more than one phase ahead).
+// The ring needs at least as many slots as matchers: gather warps release tiles strictly in order, so a matcher that
+// has filled tile t - NM knows every tile <= t - NM - ring is consumed; with ring >= NM that covers t - 2 ring, i.e. its
+// parity wait on slot t % ring is never more than one phase ahead.
 static bool bulk_layout(const EmbedParams &p, int G, int nm, int budget_bytes, BulkLayout &lay) {
     int64_t slot = p.row_stride > 2ll * p.D ? p.row_stride : 2ll * p.D;
     slot = (slot + 127) / 128 * 128;
     const int64_t per_tile = slot * G;
     int ring = (int)((budget_bytes - bulk_header_bytes(G)) / per_tile);
     if (ring > kMaxRing) ring = kMaxRing;
-    ring = ring / nm * nm;
     if (ring < 2 || ring < nm) return false;
     lay.ring = ring;
     lay.slot_bytes = (int)slot;
@@ -546,65 +547,87 @@ static int launch_bulk(EmbedParams &p, const BulkLayout &lay, cudaStream_t strea
     return launch_pdl(kern, blocks, 32 * (NM + NG), (size_t)lay.smem_bytes, stream, p, lay);
 }
 
-// Kernel selection.  Rows that fit the shared-memory ring go through the bulk-copy variant; its shape follows the
-// traffic per position (measured on B200, profiles/tune_r01.md):
-//   narrow rows (<  6 KB moved per position): 4 matcher + 4 gather warps, 3 CTAs/SM, 70 KB ring  -- matcher-hungry
-//   wide rows   (>= 6 KB moved per position): 6 matcher + 12 gather warps, 1 CTA/SM, 200 KB ring -- store-hungry
-// then 2 + 6 warps with a 70 KB ring, and finally the register-load variant for rows too wide for any ring.
+// Kernel selection (measured on B200, profiles/tune_r01.md).  Rows that fit a shared-memory ring go through the
+// bulk-copy variant; its shape follows the traffic per position:
+//   kNarrow6  < 6 KB moved, tiny rows : 6 matcher + 4 gather warps, 3 CTAs/SM, 70 KB ring  (needs >= 6 ring slots)
+//   kNarrow4  < 6 KB moved            : 4 matcher + 4 gather warps, 3 CTAs/SM, 70 KB ring  -- matcher-hungry
+//   kWide    >= 6 KB moved            : 6 matcher + 12 gather warps, 1 CTA/SM, 200 KB ring -- store-hungry
+//   kSmall   anything                 : 2 matcher + 6 gather warps, 3 CTAs/SM, 70 KB ring
+//   kLdg     rows too wide for a ring : register-load variant
+// A shape that does not fit with P lanes per position is retried with 2P, 4P (fewer positions per tile = smaller ring
+// slots) before the next shape is considered.
+enum Shape : int { kNarrow6 = 0, kNarrow4 = 1, kWide = 2, kSmall = 3, kLdg = 4 };
+constexpr int kNoFit = 1;
+
 template <int QUANT, int OUT, int P>
-static int launch(EmbedParams &p, cudaStream_t stream) {
+static int launch(EmbedParams &p, cudaStream_t stream, int shape) {
     constexpr int G = 32 / P;
     BulkLayout lay;
 #ifdef SCONE_TUNE
-    if constexpr (OUT == SCONE_OUT_BF16 && ((P == 4 && QUANT == SCONE_QUANT_INT8) || (P == 8 && QUANT == SCONE_QUANT_INT4))) {
+    if constexpr (OUT == SCONE_OUT_BF16 && P == 4 && (QUANT == SCONE_QUANT_INT8 || QUANT == SCONE_QUANT_INT4)) {
         const Variant v = variant();
-#define SCONE_V(UU, NMM, NGG, MM) \
-    if (v.kind == 0 && v.u == UU && v.nm == NMM && v.ng == NGG && v.minb == MM) return launch_ldg<QUANT, OUT, P, UU, NMM, NGG, MM>(p, stream);
-        SCONE_V(4, 4, 8, 3) SCONE_V(2, 4, 8, 4) SCONE_V(4, 1, 8, 4)
-#undef SCONE_V
 #define SCONE_B(NMM, NGG, MM)                                                                                               \
     if (v.kind == 1 && v.nm == NMM && v.ng == NGG && v.minb == MM && bulk_layout(p, G, NMM, v.smem_kb * 1024, lay))          \
         return launch_bulk<QUANT, OUT, P, NMM, NGG, MM>(p, lay, stream);
         SCONE_B(3, 6, 3) SCONE_B(4, 8, 2) SCONE_B(6, 6, 2) SCONE_B(8, 8, 1) SCONE_B(12, 12, 1) SCONE_B(6, 10, 2) SCONE_B(4, 12, 2)
-        SCONE_B(8, 16, 1) SCONE_B(12, 20, 1) SCONE_B(3, 5, 3) SCONE_B(5, 5, 3) SCONE_B(4, 6, 3) SCONE_B(6, 4, 3) SCONE_B(8, 12, 1) SCONE_B(6, 18, 1)
-        SCONE_B(4, 12, 1)
+        SCONE_B(8, 16, 1) SCONE_B(12, 20, 1) SCONE_B(3, 5, 3) SCONE_B(5, 5, 3) SCONE_B(4, 6, 3) SCONE_B(8, 12, 1) SCONE_B(6, 18, 1)
+        SCONE_B(4, 12, 1) SCONE_B(8, 4, 2) SCONE_B(6, 6, 3) SCONE_B(8, 6, 2) SCONE_B(5, 3, 4) SCONE_B(6, 2, 4)
 #undef SCONE_B
         if (v.kind == 0) return launch_ldg<QUANT, OUT, P, 4, 2, 6, 4>(p, stream);
     }
 #endif
-    if constexpr (P >= 4) {
-        const int64_t moved = 2ll * p.D + (p.row_stride < 2ll * p.D ? p.row_stride : 2ll * p.D);
-        if (moved >= 6144) {
-            if (bulk_layout(p, G, 6, 200 * 1024, lay)) return launch_bulk<QUANT, OUT, P, 6, 12, 1>(p, lay, stream);
-        } else {
+    switch (shape) {
+        case kNarrow6:
+            if (bulk_layout(p, G, 6, 70 * 1024, lay)) return launch_bulk<QUANT, OUT, P, 6, 4, 3>(p, lay, stream);
+            return kNoFit;
+        case kNarrow4:
             if (bulk_layout(p, G, 4, 70 * 1024, lay)) return launch_bulk<QUANT, OUT, P, 4, 4, 3>(p, lay, stream);
-        }
+            return kNoFit;
+        case kWide:
+            if (bulk_layout(p, G, 6, 200 * 1024, lay)) return launch_bulk<QUANT, OUT, P, 6, 12, 1>(p, lay, stream);
+            return kNoFit;
+        case kSmall:
+            if (bulk_layout(p, G, 2, 70 * 1024, lay)) return launch_bulk<QUANT, OUT, P, 2, 6, 3>(p, lay, stream);
+            return kNoFit;
+        default:
+            return launch_ldg<QUANT, OUT, P, 4, 2, 6, 4>(p, stream);
     }
-    if (bulk_layout(p, G, 2, 70 * 1024, lay)) return launch_bulk<QUANT, OUT, P, 2, 6, 3>(p, lay, stream);
-    return launch_ldg<QUANT, OUT, P, 4, 2, 6, 4>(p, stream);
 }
 
 template <int QUANT, int OUT>
-static int launch_p(int P, EmbedParams &p, cudaStream_t stream) {
+static int launch_p(int P, EmbedParams &p, cudaStream_t stream, int shape) {
     switch (P) {
-        case 1: return launch<QUANT, OUT, 1>(p, stream);
-        case 2: return launch<QUANT, OUT, 2>(p, stream);
-        case 4: return launch<QUANT, OUT, 4>(p, stream);
-        default: return launch<QUANT, OUT, 8>(p, stream);
+        case 1: return launch<QUANT, OUT, 1>(p, stream, shape);
+        case 2: return launch<QUANT, OUT, 2>(p, stream, shape);
+        case 4: return launch<QUANT, OUT, 4>(p, stream, shape);
+        default: return launch<QUANT, OUT, 8>(p, stream, shape);
     }
 }
 
-static int dispatch(int P, EmbedParams &p, int quant, int out_dtype, cudaStream_t stream) {
-    int rc;
+static int dispatch_one(int P, EmbedParams &p, int quant, int out_dtype, cudaStream_t stream, int shape) {
     if (out_dtype == SCONE_OUT_BF16) {
-        if (quant == SCONE_QUANT_FP16) rc = launch_p<SCONE_QUANT_FP16, SCONE_OUT_BF16>(P, p, stream);
-        else if (quant == SCONE_QUANT_INT8) rc = launch_p<SCONE_QUANT_INT8, SCONE_OUT_BF16>(P, p, stream);
-        else rc = launch_p<SCONE_QUANT_INT4, SCONE_OUT_BF16>(P, p, stream);
-    } else {
-        if (quant == SCONE_QUANT_FP16) rc = launch_p<SCONE_QUANT_FP16, SCONE_OUT_FP16>(P, p, stream);
-        else if (quant == SCONE_QUANT_INT8) rc = launch_p<SCONE_QUANT_INT8, SCONE_OUT_FP16>(P, p, stream);
-        else rc = launch_p<SCONE_QUANT_INT4, SCONE_OUT_FP16>(P, p, stream);
+        if (quant == SCONE_QUANT_FP16) return launch_p<SCONE_QUANT_FP16, SCONE_OUT_BF16>(P, p, stream, shape);
+        if (quant == SCONE_QUANT_INT8) return launch_p<SCONE_QUANT_INT8, SCONE_OUT_BF16>(P, p, stream, shape);
+        return launch_p<SCONE_QUANT_INT4, SCONE_OUT_BF16>(P, p, stream, shape);
     }
+    if (quant == SCONE_QUANT_FP16) return launch_p<SCONE_QUANT_FP16, SCONE_OUT_FP16>(P, p, stream, shape);
+    if (quant == SCONE_QUANT_INT8) return launch_p<SCONE_QUANT_INT8, SCONE_OUT_FP16>(P, p, stream, shape);
+    return launch_p<SCONE_QUANT_INT4, SCONE_OUT_FP16>(P, p, stream, shape);
+}
+
+// P = the fewest lanes per position the vocabulary needs.
+static int dispatch(int P, EmbedParams &p, int quant, int out_dtype, cudaStream_t stream) {
+    const int64_t moved = 2ll * p.D + (p.row_stride < 2ll * p.D ? p.row_stride : 2ll * p.D);
+    const int narrow[] = {kNarrow6, kNarrow4, kSmall}, wide[] = {kWide, kSmall};
+    const int *order = moved >= 6144 ? wide : narrow;
+    const int n_order = moved >= 6144 ? 2 : 3;
+    int rc = kNoFit;
+    for (int s = 0; s < n_order && rc == kNoFit; ++s)
+        for (int pp = P; pp <= 8 && rc == kNoFit; pp <<= 1) {
+            rc = dispatch_one(pp, p, quant, out_dtype, stream, order[s]);
+            if (order[s] == kNarrow6) break;  // only worth it at full tile size
+        }
+    if (rc == kNoFit) rc = dispatch_one(P, p, quant, out_dtype, stream, kLdg);
     if (rc != SCONE_OK) return rc;
     SCONE_LAUNCHED();
     return SCONE_OK;
@@ -669,7 +692,7 @@ int scone_embed_forward(const scone_index_t *index, const scone_table_desc_t *ta
     p.out_id = d_out_id;
     p.out_len = d_out_len;
     p.status = d_status;
-    return dispatch(lanes_per_token(ix->max_n), p, table->quant, out_dtype, stream);
+    return dispatch(lanes_per_position(ix->len_mask, ix->max_n), p, table->quant, out_dtype, stream);
 }
 
 int scone_embed_forward_sharded(const scone_index_t *index, const scone_table_desc_t *shard, const void *const *d_shard_rows,
@@ -714,7 +737,7 @@ int scone_embed_forward_sharded(const scone_index_t *index, const scone_table_de
     p.out_len = d_out_len;
     p.status = d_status;
     p.world = -world;  // negative: always go through the pointer table, even for one shard
-    return dispatch(lanes_per_token(ix->max_n), p, shard->quant, out_dtype, stream);
+    return dispatch(lanes_per_position(ix->len_mask, ix->max_n), p, shard->quant, out_dtype, stream);
 }
 
 int scone_embed_gather(const scone_table_desc_t *table, const void *d_base_emb, int64_t base_rows, const void *d_pos_emb,

@@ -95,7 +95,8 @@ __global__ void __launch_bounds__(256) lookup_kernel(IndexView ix, const int64_t
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t base = warp * G;
     if (base >= T) return;
-    WindowMatch m = match_window<P>(ix, load_window_token<P>(ids, T, base, lane), T, L, base, lane);
+    const int back = ix.max_n - 1;
+    WindowMatch m = match_window<P>(ix, load_window_token<P>(ids, T, base, lane, back), T, L, base, lane, back);
     const int j = lane / P;
     if ((lane % P) == 0 && base + j < T) {
         if (out_id) out_id[base + j] = m.fid;
@@ -111,12 +112,14 @@ __global__ void __launch_bounds__(256) match_all_kernel(IndexView ix, const int6
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t base = warp * G;
     if (base >= T) return;
-    int32_t fid = candidate_id<P>(ix, load_window_token<P>(ids, T, base, lane), T, L, base, lane, /*use_len_mask=*/true);
-    const int j = lane / P, n1 = lane % P;
+    const int back = ix.max_n - 1;
+    const int j = lane / P, n1 = lane % P;  // dense mapping: candidate n1 is length n1 + 1
+    const bool present = n1 < ix.max_n && ((ix.len_mask >> n1) & 1u);
+    int32_t fid = candidate_id<P>(ix, load_window_token<P>(ids, T, base, lane, back), T, L, base, lane, present ? n1 + 1 : 0, back);
     if (n1 < ix.max_n && base + j < T) out[(base + j) * ix.max_n + n1] = fid;
 }
 
-static int lanes_per_token(int max_n) { return max_n <= 1 ? 1 : max_n <= 2 ? 2 : max_n <= 4 ? 4 : 8; }
+static int lanes_dense(int max_n) { return max_n <= 1 ? 1 : max_n <= 2 ? 2 : max_n <= 4 ? 4 : 8; }
 
 }  // namespace scone
 
@@ -226,7 +229,7 @@ int scone_index_lookup(const scone_index_t *index, const int64_t *d_ids, int64_t
     SCONE_REQUIRE(T < (1ll << 40), "scone_index_lookup: batch too large");
     const scone_index_impl *ix = reinterpret_cast<const scone_index_impl *>(index);
     IndexView v{ix->slots, ix->cap, ix->len_mask, ix->max_n};
-    const int P = lanes_per_token(ix->max_n);
+    const int P = lanes_per_position(ix->len_mask, ix->max_n);
     const int64_t windows = (T + (32 / P) - 1) / (32 / P);
     const unsigned blocks = (unsigned)((windows + 7) / 8);
     switch (P) {
@@ -249,7 +252,7 @@ int scone_index_match_all(const scone_index_t *index, const int64_t *d_ids, int6
     SCONE_REQUIRE(d_ids && d_out, "scone_index_match_all: NULL buffer");
     const scone_index_impl *ix = reinterpret_cast<const scone_index_impl *>(index);
     IndexView v{ix->slots, ix->cap, ix->len_mask, ix->max_n};
-    const int P = lanes_per_token(ix->max_n);
+    const int P = lanes_dense(ix->max_n);
     const int64_t windows = (T + (32 / P) - 1) / (32 / P);
     const unsigned blocks = (unsigned)((windows + 7) / 8);
     switch (P) {

@@ -133,3 +133,41 @@ def test_header_cites_reference_for_every_entry_point():
         if sym.startswith(("scone_index", "scone_table", "scone_embed", "scone_pipeline", "scone_host")):
             stem = sym if sym in integration else sym.rsplit("_", 1)[0]
             assert stem in integration, sym
+
+
+def test_host_gather_rows_is_pure_host_code():
+    """scone_host_gather_rows (staged offload tier) runs without a GPU: multi-threaded row gather into a staging buffer."""
+    from scone_b200 import _lib
+    L = _lib.load()
+    rng = np.random.default_rng(0)
+    table = rng.integers(0, 256, size=(1000, 96), dtype=np.uint8)
+    ids = rng.integers(0, 1000, size=777).astype(np.int32)
+    for threads in (1, 3, 16):
+        out = np.zeros((777, 96), dtype=np.uint8)
+        rc = L.scone_host_gather_rows(table.ctypes.data, 96, 1000, ids.ctypes.data, 777, out.ctypes.data, threads)
+        assert rc == 0 and np.array_equal(out, table[ids])
+    bad = ids.copy()
+    bad[5] = 1000
+    assert L.scone_host_gather_rows(table.ctypes.data, 96, 1000, bad.ctypes.data, 777, out.ctypes.data, 4) == _lib.E_INVALID
+    assert b"outside" in L.scone_last_error()
+    assert L.scone_host_gather_rows(table.ctypes.data, 96, 1000, ids.ctypes.data, 0, out.ctypes.data, 4) == 0
+
+
+def test_c_abi_rejects_bad_arguments_without_a_gpu():
+    """Argument validation happens before any CUDA call, so it can be exercised here."""
+    import ctypes as C
+    from scone_b200 import _lib
+    L = _lib.load()
+    rs, so = C.c_int64(), C.c_int32()
+    assert L.scone_table_layout(1, 1024, 128, 0, C.byref(rs), C.byref(so)) == 0 and (rs.value, so.value) == (1056, 1024)
+    assert L.scone_table_layout(2, 4096, 128, 128, C.byref(rs), C.byref(so)) == 0 and (rs.value, so.value) == (2176, 2048)
+    assert L.scone_table_layout(7, 1024, 128, 0, C.byref(rs), C.byref(so)) == _lib.E_INVALID
+    assert L.scone_table_layout(2, 1000, 128, 0, C.byref(rs), C.byref(so)) == _lib.E_INVALID
+    h = C.c_void_p()
+    assert L.scone_index_create(None, None, 5, 9, 0.5, None, C.byref(h)) == _lib.E_INVALID        # max_n > 7
+    assert b"max_n" in L.scone_last_error()
+    assert L.scone_index_create(None, None, 5, 3, 0.95, None, C.byref(h)) == _lib.E_INVALID       # load factor
+    assert L.scone_index_lookup(None, None, 1, 1, None, None, None) == _lib.E_INVALID
+    assert L.scone_index_destroy(None) == 0 and L.scone_pipeline_destroy(None) == 0
+    desc = _lib.TableDesc(16, 100, 4, 1, 1024, 128, 1024)                                         # row_stride 100: not a multiple of 16
+    assert L.scone_table_gather(C.byref(desc), None, 1, None, 2, None, None) == _lib.E_INVALID

@@ -44,7 +44,11 @@ def main():
     for a in sys.argv[1:]:
         if a.startswith("--variants="):
             variants = a.split("=", 1)[1].split(",")
-    w = bench.WORKLOADS[name]
+    if name.startswith("custom:"):      # custom:D:quant:max_n:N:B:L:V
+        _, D_, q_, mn_, N_, B_, L_, V_ = name.split(":")
+        w = dict(N=int(N_), D=int(D_), V=int(V_), max_n=int(mn_), quant=q_, B=int(B_), L=int(L_), desc=name)
+    else:
+        w = bench.WORKLOADS[name]
     dev = torch.device("cuda", 0)
     B, L, D, N, V = w["B"], w["L"], w["D"], w["N"], w["V"]
     T = B * L
@@ -93,7 +97,7 @@ def main():
         report("fused kind:U:NM:NG:MINB:KB=" + v, graph_time(lambda k: sb.embed_forward(index, table, base, batches[k % 8], out=out, out_id=out_id, out_len=out_len)))
     os.environ.pop("SCONE_EMBED_VARIANT", None)
     os.makedirs("gpurun_out", exist_ok=True)
-    json.dump(res, open(f"gpurun_out/tune_{name}.json", "w"), indent=1)
+    json.dump(res, open("gpurun_out/tune_" + name.replace(":", "_") + ".json", "w"), indent=1)
 
 
 if __name__ == "__main__":
