@@ -65,7 +65,7 @@ typedef struct scone_index_info {
     int32_t max_n;
     uint32_t len_mask;   /* bit (n-1) set when some f-gram has length n */
     int32_t max_probe;   /* longest insert probe sequence seen at build time */
-    int32_t slot_bytes;  /* 32 */
+    int32_t slot_bytes;  /* 32, or 16 for the compact format (all tokens < 65535 and max_n <= 6) */
 } scone_index_info_t;
 
 /* Where the cache rows live and how they are encoded.  Row r starts at
@@ -94,8 +94,10 @@ const char *scone_last_error(void);
  * The open-addressing table (32-byte slots, key stored inline, home slot from a
  * rolling 64-bit hash) is built by kernels on `stream`; the call then reads back a
  * build audit and fails with SCONE_E_VOCAB if two rows hold the same f-gram, a length
- * is outside [1, max_n] or a token is negative.  load_factor in (0, 0.9]; <= 0 -> 0.25 (128 B of index per
- * f-gram: short probe chains matter more than index size). */
+ * is outside [1, max_n] or a token is negative.  When every token is < 65535 and max_n <= 6 the compact
+ * 16-byte slot format is used (four slots per 64-byte probe).  load_factor in (0, 0.9]; <= 0 -> 0.25 (128 B of
+ * index per f-gram with 32-byte slots, 64 B with compact slots): short probe chains matter more than index size,
+ * see DESIGN.md. */
 int scone_index_create(const int32_t *d_tokens, const uint8_t *d_lens, int64_t n, int32_t max_n,
                        double load_factor, void *stream, scone_index_t **out);
 int scone_index_destroy(scone_index_t *index);

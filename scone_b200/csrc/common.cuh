@@ -58,13 +58,23 @@ struct __align__(32) Slot {
 };
 static_assert(sizeof(Slot) == 32, "slot must be one sector");
 
+// Compact slot format, used when every vocabulary token is < 65535 and max_n <= 6 (e.g. GPT-2's 50 257 tokens):
+// 16 bytes = id + six 16-bit tokens (reverse order, 0xFFFF padded).  Four slots per 64-byte block, half the index
+// bytes per f-gram: a 1 M f-gram index is 32 MB at load factor 0.5 and stays resident in the 126 MB L2.
+struct __align__(16) Slot16 {
+    int32_t id;
+    uint32_t t[3];
+};
+static_assert(sizeof(Slot16) == 16, "compact slot");
+
 struct scone_index_impl {
-    Slot *slots;
+    Slot *slots;  // Slot or Slot16 array, `cap` entries
     uint64_t cap;
     int64_t n;
     int32_t max_n;
     uint32_t len_mask;
     int32_t max_probe;
+    int32_t compact;
     int device;
 };
 
@@ -74,7 +84,10 @@ struct IndexView {
     uint64_t cap;
     uint32_t len_mask;
     int32_t max_n;
+    int32_t compact;
 };
+
+inline IndexView view_of(const scone_index_impl *ix) { return IndexView{ix->slots, ix->cap, ix->len_mask, ix->max_n, ix->compact}; }
 
 // ---------------------------------------------------------------------------------------------
 // rolling 64-bit hash of the n-gram ENDING at a position: tokens are folded last-to-first, so
@@ -133,6 +146,45 @@ __device__ __forceinline__ int32_t probe(const IndexView &ix, uint64_t h, const 
         if (s == ix.cap) s = 0;
     }
     return -1;
+}
+
+// compact format: home slots are multiples of 4, a probe step reads the whole 64-byte block (four slots)
+__device__ __forceinline__ uint64_t home_slot16(uint64_t h, uint64_t cap) { return __umul64hi(h, cap >> 2) << 2; }
+
+__device__ __forceinline__ bool pack_key16(const int32_t (&key)[7], uint32_t (&k)[3]) {
+    bool ok = key[6] < 0;  // at most six tokens
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const int32_t lo = key[2 * i], hi = key[2 * i + 1];
+        ok = ok && lo < 0xFFFF && hi < 0xFFFF;
+        k[i] = (uint32_t)(lo < 0 ? 0xFFFF : lo) | ((uint32_t)(hi < 0 ? 0xFFFF : hi) << 16);
+    }
+    return ok;
+}
+
+__device__ __forceinline__ int32_t probe16(const IndexView &ix, uint64_t h, const int32_t (&key)[7]) {
+    uint32_t k[3];
+    if (!pack_key16(key, k)) return -1;  // a token >= 65535 cannot be in a compact vocabulary
+    const Slot16 *slots = reinterpret_cast<const Slot16 *>(ix.slots);
+    uint64_t s = home_slot16(h, ix.cap);
+    for (uint64_t it = 0; it < ix.cap; it += 4) {
+        int32_t a[8], b[8];
+        load_slot(reinterpret_cast<const Slot *>(slots + s), a);      // slots s, s+1
+        load_slot(reinterpret_cast<const Slot *>(slots + s + 2), b);  // slots s+2, s+3
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int32_t *w = (q < 2 ? a : b) + 4 * (q & 1);
+            if (w[0] < 0) return -1;
+            if ((uint32_t)w[1] == k[0] && (uint32_t)w[2] == k[1] && (uint32_t)w[3] == k[2]) return w[0];
+        }
+        s += 4;
+        if (s == ix.cap) s = 0;
+    }
+    return -1;
+}
+
+__device__ __forceinline__ int32_t probe_any(const IndexView &ix, uint64_t h, const int32_t (&key)[7]) {
+    return ix.compact ? probe16(ix, h, key) : probe(ix, h, key);
 }
 
 // ---------------------------------------------------------------------------------------------

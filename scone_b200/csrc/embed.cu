@@ -680,7 +680,7 @@ int scone_embed_forward(const scone_index_t *index, const scone_table_desc_t *ta
     EmbedParams p{};
     int rc = fill_table(p, table, "scone_embed_forward");
     if (rc != SCONE_OK) return rc;
-    p.ix = IndexView{ix->slots, ix->cap, ix->len_mask, ix->max_n};
+    p.ix = view_of(ix);
     p.fgram_in = nullptr;
     p.base = static_cast<const uint8_t *>(d_base_emb);
     p.V = base_rows;
@@ -724,7 +724,7 @@ int scone_embed_forward_sharded(const scone_index_t *index, const scone_table_de
     p.shard_rows = reinterpret_cast<const uint8_t *const *>(d_shard_rows);
     p.rows = nullptr;
     p.num_rows = total_rows;
-    p.ix = IndexView{ix->slots, ix->cap, ix->len_mask, ix->max_n};
+    p.ix = view_of(ix);
     p.fgram_in = nullptr;
     p.base = static_cast<const uint8_t *>(d_base_emb);
     p.V = base_rows;

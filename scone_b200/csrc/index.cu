@@ -3,6 +3,9 @@
 // Takes over the Python set / dict of int tuples of the reference's NGramExtractor
 // (scone/tokenization/n_gram_extractor.py:41-44, :96-99, :121-122) and the tuple -> id lookup of
 // scone/inference/embedding_cache.py:173.
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
 #include "match.cuh"
 
@@ -15,12 +18,12 @@ struct BuildStats {
     unsigned long long dup;
     unsigned int len_mask;
     int max_probe;
+    int max_tok;
 };
 
-// One thread per f-gram: claim the first free slot of its probe sequence with a CAS on the id
-// word, then fill in the key.  No lookup runs concurrently with the build.
-__global__ void __launch_bounds__(256) index_build_kernel(const int32_t *__restrict__ tokens, const uint8_t *__restrict__ lens,
-                                                          int64_t n, int32_t max_n, Slot *slots, uint64_t cap, BuildStats *stats) {
+// First pass: validate the vocabulary and find the largest token (decides the slot format).
+__global__ void __launch_bounds__(256) index_scan_kernel(const int32_t *__restrict__ tokens, const uint8_t *__restrict__ lens, int64_t n,
+                                                         int32_t max_n, BuildStats *stats) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int len = lens[i];
@@ -28,6 +31,26 @@ __global__ void __launch_bounds__(256) index_build_kernel(const int32_t *__restr
         atomicAdd(&stats->bad_len, 1ull);
         return;
     }
+    int mx = 0;
+    bool bad = false;
+    for (int k = 0; k < len; ++k) {
+        const int32_t t = tokens[i * max_n + k];
+        bad |= t < 0;
+        mx = t > mx ? t : mx;
+    }
+    if (bad) atomicAdd(&stats->bad_tok, 1ull);
+    else atomicMax(&stats->max_tok, mx);
+}
+
+// One thread per f-gram: claim the first free slot of its probe sequence with a CAS on the id
+// word, then fill in the key.  No lookup runs concurrently with the build.
+__global__ void __launch_bounds__(256) index_build_kernel(const int32_t *__restrict__ tokens, const uint8_t *__restrict__ lens,
+                                                          int64_t n, int32_t max_n, Slot *slots, uint64_t cap, int compact,
+                                                          BuildStats *stats) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int len = lens[i];
+    if (len < 1 || len > max_n) return;  // counted by the scan
     int32_t key[7];
     uint64_t h = hash_seed();
     bool bad = false;
@@ -41,21 +64,33 @@ __global__ void __launch_bounds__(256) index_build_kernel(const int32_t *__restr
             h = hash_roll(h, (uint32_t)t);
         }
     }
-    if (bad) {
-        atomicAdd(&stats->bad_tok, 1ull);
-        return;
-    }
+    if (bad) return;  // counted by the scan
     h = hash_finish(h, len);
-    uint64_t s = home_slot(h, cap);
     int probes = 1;
-    for (;;) {
-        int32_t old = atomicCAS(&slots[s].w[0], -1, (int32_t)i);
-        if (old == -1) break;
-        if (++s == cap) s = 0;
-        ++probes;
-    }
+    if (compact) {
+        Slot16 *s16 = reinterpret_cast<Slot16 *>(slots);
+        uint64_t s = home_slot16(h, cap);
+        for (;;) {
+            int32_t old = atomicCAS(&s16[s].id, -1, (int32_t)i);
+            if (old == -1) break;
+            if (++s == cap) s = 0;
+            ++probes;
+        }
+        uint32_t k16[3];
+        pack_key16(key, k16);
 #pragma unroll
-    for (int k = 0; k < 7; ++k) slots[s].w[k + 1] = key[k];
+        for (int k = 0; k < 3; ++k) s16[s].t[k] = k16[k];
+    } else {
+        uint64_t s = home_slot(h, cap);
+        for (;;) {
+            int32_t old = atomicCAS(&slots[s].w[0], -1, (int32_t)i);
+            if (old == -1) break;
+            if (++s == cap) s = 0;
+            ++probes;
+        }
+#pragma unroll
+        for (int k = 0; k < 7; ++k) slots[s].w[k + 1] = key[k];
+    }
     atomicOr(&stats->len_mask, 1u << (len - 1));
     atomicMax(&stats->max_probe, probes);
 }
@@ -81,7 +116,7 @@ __global__ void __launch_bounds__(256) index_audit_kernel(const int32_t *__restr
         }
     }
     h = hash_finish(h, len);
-    if (probe(ix, h, key) != (int32_t)i) atomicAdd(&stats->dup, 1ull);
+    if (probe_any(ix, h, key) != (int32_t)i) atomicAdd(&stats->dup, 1ull);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -135,40 +170,56 @@ int scone_index_create(const int32_t *d_tokens, const uint8_t *d_lens, int64_t n
     SCONE_REQUIRE(n >= 0 && n < (int64_t)0x7FFFFFFF, "scone_index_create: n = %lld outside [0, 2^31-1)", (long long)n);
     SCONE_REQUIRE(max_n >= 1 && max_n <= SCONE_MAX_N, "scone_index_create: max_n = %d outside [1, %d]", max_n, SCONE_MAX_N);
     SCONE_REQUIRE(n == 0 || (d_tokens && d_lens), "scone_index_create: NULL vocabulary arrays");
-    if (!(load_factor > 0.0)) load_factor = 0.25;
-    SCONE_REQUIRE(load_factor <= 0.9, "scone_index_create: load_factor %.3f > 0.9", load_factor);
+    SCONE_REQUIRE(!(load_factor > 0.9), "scone_index_create: load_factor %.3f > 0.9", load_factor);
 
     scone_index_impl *ix = new (std::nothrow) scone_index_impl();
     if (!ix) {
         set_error("scone_index_create: out of host memory");
         return SCONE_E_NOMEM;
     }
-    SCONE_CUDA(cudaGetDevice(&ix->device));
     ix->n = n;
     ix->max_n = max_n;
-    uint64_t cap = (uint64_t)((double)n / load_factor) + 1;
-    if (cap < 64) cap = 64;
-    cap = (cap + 3) & ~3ull;  // whole 128-byte lines
-    ix->cap = cap;
     BuildStats *d_stats = nullptr;
     BuildStats h{};
-    cudaError_t e = cudaMalloc(&ix->slots, cap * sizeof(Slot));
-    if (e == cudaSuccess) e = cudaMalloc(&d_stats, sizeof(BuildStats));
-    if (e != cudaSuccess) {
-        set_error("scone_index_create: cudaMalloc of %llu slot bytes failed: %s", (unsigned long long)(cap * sizeof(Slot)),
-                  cudaGetErrorString(e));
-        if (ix->slots) cudaFree(ix->slots);
-        delete ix;
-        return e == cudaErrorMemoryAllocation ? SCONE_E_NOMEM : SCONE_E_CUDA;
-    }
+    const unsigned blocks = (unsigned)((n + 255) / 256);
     int rc = [&]() -> int {
-        SCONE_CUDA(cudaMemsetAsync(ix->slots, 0xFF, cap * sizeof(Slot), stream));
+        SCONE_CUDA(cudaGetDevice(&ix->device));
+        SCONE_CUDA(cudaMalloc(&d_stats, sizeof(BuildStats)));
         SCONE_CUDA(cudaMemsetAsync(d_stats, 0, sizeof(BuildStats), stream));
+        // pass 1: validate, find the largest token -> slot format
         if (n > 0) {
-            const unsigned blocks = (unsigned)((n + 255) / 256);
-            index_build_kernel<<<blocks, 256, 0, stream>>>(d_tokens, d_lens, n, max_n, ix->slots, cap, d_stats);
+            index_scan_kernel<<<blocks, 256, 0, stream>>>(d_tokens, d_lens, n, max_n, d_stats);
             SCONE_LAUNCHED();
-            IndexView v{ix->slots, cap, 0xFFFFFFFFu, max_n};
+        }
+        SCONE_CUDA(cudaMemcpyAsync(&h, d_stats, sizeof h, cudaMemcpyDeviceToHost, stream));
+        SCONE_CUDA(cudaStreamSynchronize(stream));
+        if (h.bad_len || h.bad_tok) return SCONE_OK;  // reported below
+        const char *fmt = getenv("SCONE_INDEX_FORMAT");  // "wide" / "compact" override the automatic choice (testing)
+        ix->compact = (max_n <= 6 && h.max_tok < 0xFFFF) ? 1 : 0;
+        if (fmt && !strcmp(fmt, "wide")) ix->compact = 0;
+        if (fmt && !strcmp(fmt, "compact") && !(max_n <= 6 && h.max_tok < 0xFFFF)) {
+            set_error("scone_index_create: SCONE_INDEX_FORMAT=compact needs max_n <= 6 and tokens < 65535");
+            return SCONE_E_INVALID;
+        }
+        // default load factor 0.25 for both formats (measured: compact at 0.5 costs config 1 a microsecond of probe chain)
+        const double lf = load_factor > 0.0 ? load_factor : 0.25;
+        uint64_t cap = (uint64_t)((double)n / lf) + 1;
+        if (cap < 64) cap = 64;
+        cap = (cap + 3) & ~3ull;  // whole 64-byte blocks of either format
+        ix->cap = cap;
+        const size_t bytes = cap * (ix->compact ? sizeof(Slot16) : sizeof(Slot));
+        cudaError_t e = cudaMalloc(&ix->slots, bytes);
+        if (e != cudaSuccess) {
+            set_error("scone_index_create: cudaMalloc of %llu slot bytes failed: %s", (unsigned long long)bytes, cudaGetErrorString(e));
+            ix->slots = nullptr;
+            return e == cudaErrorMemoryAllocation ? SCONE_E_NOMEM : SCONE_E_CUDA;
+        }
+        SCONE_CUDA(cudaMemsetAsync(ix->slots, 0xFF, bytes, stream));
+        // pass 2: insert, then every f-gram looks itself up (duplicate audit)
+        if (n > 0) {
+            index_build_kernel<<<blocks, 256, 0, stream>>>(d_tokens, d_lens, n, max_n, ix->slots, cap, ix->compact, d_stats);
+            SCONE_LAUNCHED();
+            IndexView v{ix->slots, cap, 0xFFFFFFFFu, max_n, ix->compact};
             index_audit_kernel<<<blocks, 256, 0, stream>>>(d_tokens, d_lens, n, max_n, v, d_stats);
             SCONE_LAUNCHED();
         }
@@ -176,14 +227,14 @@ int scone_index_create(const int32_t *d_tokens, const uint8_t *d_lens, int64_t n
         SCONE_CUDA(cudaStreamSynchronize(stream));
         return SCONE_OK;
     }();
-    cudaFree(d_stats);
+    if (d_stats) cudaFree(d_stats);
     if (rc == SCONE_OK && (h.bad_len || h.bad_tok || h.dup)) {
         set_error("scone_index_create: vocabulary rejected: %llu duplicated f-grams, %llu lengths outside [1, %d], %llu rows with negative tokens",
                   h.dup, h.bad_len, max_n, h.bad_tok);
         rc = SCONE_E_VOCAB;
     }
     if (rc != SCONE_OK) {
-        cudaFree(ix->slots);
+        if (ix->slots) cudaFree(ix->slots);
         delete ix;
         return rc;
     }
@@ -210,11 +261,11 @@ int scone_index_info(const scone_index_t *index, scone_index_info_t *info) {
     const scone_index_impl *ix = reinterpret_cast<const scone_index_impl *>(index);
     info->num_fgrams = ix->n;
     info->capacity = (int64_t)ix->cap;
-    info->bytes = (int64_t)(ix->cap * sizeof(Slot));
+    info->bytes = (int64_t)(ix->cap * (ix->compact ? sizeof(Slot16) : sizeof(Slot)));
     info->max_n = ix->max_n;
     info->len_mask = ix->len_mask;
     info->max_probe = ix->max_probe;
-    info->slot_bytes = (int32_t)sizeof(Slot);
+    info->slot_bytes = (int32_t)(ix->compact ? sizeof(Slot16) : sizeof(Slot));
     return SCONE_OK;
 }
 
@@ -228,7 +279,7 @@ int scone_index_lookup(const scone_index_t *index, const int64_t *d_ids, int64_t
     SCONE_REQUIRE(d_ids, "scone_index_lookup: NULL ids");
     SCONE_REQUIRE(T < (1ll << 40), "scone_index_lookup: batch too large");
     const scone_index_impl *ix = reinterpret_cast<const scone_index_impl *>(index);
-    IndexView v{ix->slots, ix->cap, ix->len_mask, ix->max_n};
+    IndexView v = view_of(ix);
     const int P = lanes_per_position(ix->len_mask, ix->max_n);
     const int64_t windows = (T + (32 / P) - 1) / (32 / P);
     const unsigned blocks = (unsigned)((windows + 7) / 8);
@@ -251,7 +302,7 @@ int scone_index_match_all(const scone_index_t *index, const int64_t *d_ids, int6
     if (T == 0) return SCONE_OK;
     SCONE_REQUIRE(d_ids && d_out, "scone_index_match_all: NULL buffer");
     const scone_index_impl *ix = reinterpret_cast<const scone_index_impl *>(index);
-    IndexView v{ix->slots, ix->cap, ix->len_mask, ix->max_n};
+    IndexView v = view_of(ix);
     const int P = lanes_dense(ix->max_n);
     const int64_t windows = (T + (32 / P) - 1) / (32 / P);
     const unsigned blocks = (unsigned)((windows + 7) / 8);

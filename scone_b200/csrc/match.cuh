@@ -74,7 +74,7 @@ __device__ __forceinline__ int32_t candidate_id(const IndexView &ix, int32_t tok
         }
     }
     if (!cand) return -1;
-    return probe(ix, hash_finish(h, n), key);
+    return probe_any(ix, hash_finish(h, n), key);
 }
 
 // Longest hit of the lane's position (compact mapping); every lane of a P-lane group returns the same value.

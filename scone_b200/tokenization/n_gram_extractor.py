@@ -242,7 +242,7 @@ class NGramExtractor:
         return self
 
     # ---- device index -----------------------------------------------------------------------------
-    def device_index(self, device: Optional[torch.device] = None, load_factor: float = 0.25) -> FGramIndex:
+    def device_index(self, device: Optional[torch.device] = None, load_factor: float = 0.0) -> FGramIndex:
         """The GPU hash index of the current vocabulary (built once, cached)."""
         dev = torch.device(device) if device is not None else (torch.device(self.device) if self.device else _default_device())
         if dev.type != "cuda":

@@ -18,6 +18,17 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
+@pytest.fixture(autouse=True, params=["auto", "wide"])
+def index_format(request, monkeypatch):
+    """Every test runs with the automatic slot format (compact 16-byte slots whenever the tokens allow) and with the
+    32-byte format forced."""
+    if request.param == "wide":
+        monkeypatch.setenv("SCONE_INDEX_FORMAT", "wide")
+    else:
+        monkeypatch.delenv("SCONE_INDEX_FORMAT", raising=False)
+    return request.param
+
+
 def _mods():
     import scone_b200
     from scone_b200.utils import synthetic
@@ -96,6 +107,15 @@ def test_index_build_audit():
     e = _index(np.zeros((0, 3), np.int32), np.zeros((0,), np.uint8))
     assert e.lookup(torch.tensor([[1, 2, 3]], device=DEV))[0].tolist() == [[-1, -1, -1]]
     assert e.len_mask == 0
+    # slot format: compact when every token < 65535 and max_n <= 6, unless forced wide
+    import os
+    small = _index(np.array([[1, 2]], np.int32), np.array([2], np.uint8))
+    big = _index(np.array([[1, 70000]], np.int32), np.array([2], np.uint8))
+    assert small.slot_bytes == (32 if os.environ.get("SCONE_INDEX_FORMAT") == "wide" else 16) and big.slot_bytes == 32
+    fid, _ = big.lookup(torch.tensor([[1, 70000, 65535, 1, 70000]], device=DEV))
+    assert fid.tolist() == [[-1, 0, -1, -1, 0]]
+    fid, _ = small.lookup(torch.tensor([[1, 2, 65535, 65536 + 1, 2, 1, 2]], device=DEV))     # 65537 must not alias token 1
+    assert fid.tolist() == [[-1, 0, -1, -1, -1, -1, 0]]
 
 
 def test_lookup_edge_shapes_and_ids():

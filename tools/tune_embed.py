@@ -53,9 +53,9 @@ def main():
     B, L, D, N, V = w["B"], w["L"], w["D"], w["N"], w["V"]
     T = B * L
     toks, lens, longest = S.make_vocab_device(N, w["max_n"], V, seed=0, device=dev, return_longest=True)
-    lf = float(os.environ.get("LF", "0.5"))
+    lf = float(os.environ.get("LF", "0"))
     index = sb.FGramIndex(toks, lens, load_factor=lf)
-    print(json.dumps({"load_factor": lf, "index_MB": index.bytes / 1e6, "max_probe": index.max_probe}))
+    print(json.dumps({"load_factor": lf, "index_MB": index.bytes / 1e6, "max_probe": index.max_probe, "slot_bytes": index.slot_bytes}))
     table = sb.CacheTable(N, D, w["quant"], device=dev)
     S.fill_table_device(table, seed=2)
     base = S.make_base_device(V, D, torch.bfloat16, seed=3, device=dev)
