@@ -6,17 +6,21 @@
 // scone/inference/embedding_cache.py:149-181, scone/inference/engine.py:235-266,
 // scone/models/language_model.py:239-243), with Algorithm-2 (replace-or-fallback) semantics.
 //
-// Shape of the kernel (HBM-bound gather, no tensor cores):
-//   * persistent CTAs (a multiple of the 148 SMs), each 1 MATCHER warp + 8 GATHER warps.
-//   * the matcher walks the CTA's tiles (a tile = the G = 32/P consecutive positions one warp can match
-//     at once, match.cuh), resolves their f-gram ids and pushes (row id, fallback token) into a small
-//     shared-memory ring guarded by mbarriers.  It runs up to kRing tiles ahead, so the dependent
+// Shape of the kernels (HBM-bound gather, no tensor cores):
+//   * persistent CTAs (a multiple of the 148 SMs), warp-specialised into NM MATCHER warps and NG GATHER warps.
+//   * a matcher walks every NM-th tile of its CTA (a tile = the G = 32/P consecutive positions one warp can match
+//     at once, match.cuh), resolves the f-gram ids, writes fgram_id / match_len, and pushes (row id, fallback token)
+//     into a small shared-memory ring guarded by mbarriers.  Matchers run ahead of the gather warps, so the dependent
 //     chain ids -> hash -> slot -> (re-probe) is off the streaming warps' critical path.
-//   * a gather warp pops one position at a time and streams its row: each lane owns 8 consecutive
-//     elements (one 16 B output vector) per 256-element step, U steps are loaded back to back before
-//     any is converted.  Cache / fallback rows are read with ld.global.nc.L1::no_allocate (touched
-//     once), the output is written with 128-bit st.global.cs; slots use default caching so the much
-//     smaller index stays L2-resident.
+//   * embed_bulk_kernel (default): the matcher also issues ONE TMA bulk copy (cp.async.bulk, global -> shared) per
+//     position -- the table row on a hit, the fallback row on a miss -- into the tile's ring slot; the slot's mbarrier
+//     completes when the bytes have landed.  Loads in flight are bounded by shared memory, not registers.  Gather warps
+//     read the row from shared memory, dequantise, and write 128-bit vectors.
+//   * embed_kernel (rows too wide for a ring): gather warps load the row themselves with 128-bit
+//     ld.global.nc.L1::no_allocate, U 256-element steps in flight per lane.
+//   * everything streamed (rows, fallback rows, output) carries an L2 evict-first policy, index slots evict-last.
+//   * every gather warp waits for and releases every tile, in order: with parity-only mbarriers no waiter may be more
+//     than one phase away from the barrier's current phase.
 #include <cstdlib>
 
 #include "common.cuh"
