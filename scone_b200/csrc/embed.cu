@@ -540,10 +540,12 @@ template <int QUANT, int OUT, int P, int NM, int NG, int MINB>
 static int launch_bulk(EmbedParams &p, const BulkLayout &lay, cudaStream_t stream) {
     constexpr int G = 32 / P;
     auto kern = embed_bulk_kernel<QUANT, OUT, P, NM, NG, MINB>;
-    static int configured = 0;
-    if (configured < lay.smem_bytes) {
+    static int configured[64] = {0};  // per device: the attribute lives in the device's context
+    int dev = 0;
+    SCONE_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || configured[dev] < lay.smem_bytes) {
         SCONE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.smem_bytes));
-        configured = lay.smem_bytes;
+        if (dev >= 0 && dev < 64) configured[dev] = lay.smem_bytes;
     }
     p.num_tiles = (p.T + G - 1) / G;
     const int64_t resident = (int64_t)num_sms() * MINB;
