@@ -245,6 +245,13 @@ def run_ours(args, w, rank, local_rank, world):
     table = sb.CacheTable(N, D, w["quant"], device=dev)
     S.fill_table_device(table, seed=2)
     base = S.make_base_device(V, D, torch.bfloat16, seed=3, device=dev)
+    if args.id_dist == "zipf":
+        # secondary workload: planted f-gram ids follow a Zipf-like law instead of being uniform over the
+        # table, so hot rows hit L2 and the algorithmic GB/s exceeds the DRAM GB/s
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(7)
+        ranks = S.zipf_like_torch(gen, (8 * T,), longest.numel(), dev)
+        longest = longest[ranks]
     batches = [S.make_stream_device(toks, lens, B, L, V, seed=100 + rank * N_BATCHES + k, p_plant=1.0, pick_ids=longest)
                for k in range(N_BATCHES)]
     del toks, lens
@@ -295,6 +302,14 @@ def run_ours(args, w, rank, local_rank, world):
             stream.synchronize()
             barrier()
             ms = e0.elapsed_time(e1)
+            repeats = []
+            for _ in range(4):                       # variance only; `value` is the ONE timed replay above
+                r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                r0.record(stream)
+                graph.replay()
+                r1.record(stream)
+                stream.synchronize()
+                repeats.append(r0.elapsed_time(r1) / args.steps)
             for _ in range(reps):
                 graph.replay()
             stream.synchronize()
@@ -424,11 +439,12 @@ def run_ours(args, w, rank, local_rank, world):
 
     line = {
         "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-        "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": kernel_ms, "ms_per_step_repeats": repeats, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": f"{w['quant']}->bf16", "data": "synthetic",
         "config": {"workload": w["desc"], "f_grams": N, "dim": D, "max_n": w["max_n"], "quant": w["quant"], "batch": [B, L],
                    "per_gpu_batch": [B, L], "parallelism": f"replicas x{world} (table fits one GPU; no data-path collective)",
-                   "hit_rate": hit, "index_bytes": index.bytes, "table_bytes": table.bytes,
+                   "hit_rate": hit, "id_dist": args.id_dist, "index_bytes": index.bytes, "index_slot_bytes": index.slot_bytes,
+                   "table_bytes": table.bytes,
                    "l2": f"inputs > L2: {N_BATCHES} rotating id batches gather rows uniformly from a {table.bytes / 1e9:.2f} GB "
                          f"table and each step writes {T * D * 2 / 1e6:.0f} MB of output; no explicit flush",
                    "timing": "K steps captured in one CUDA graph, CUDA events on the launching stream, max over ranks"},
@@ -656,6 +672,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--id-dist", default="uniform", choices=["uniform", "zipf"],
+                    help="distribution of the planted f-gram ids over the table: uniform (primary, worst case for caches) or Zipf-like")
     ap.add_argument("--rows-per-gpu", type=int, default=0, help="config4/5: table rows per GPU (default: the named size / what host RAM allows)")
     ap.add_argument("--sharded-mode", default="peer", choices=["peer", "nccl"], help="config4: peer-direct fused kernel or NCCL all-to-all")
     ap.add_argument("--host-fraction", type=float, default=0.0, help="config5: fraction of host RAM to pin (default 0.5)")

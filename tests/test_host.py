@@ -171,3 +171,22 @@ def test_c_abi_rejects_bad_arguments_without_a_gpu():
     assert L.scone_index_destroy(None) == 0 and L.scone_pipeline_destroy(None) == 0
     desc = _lib.TableDesc(16, 100, 4, 1, 1024, 128, 1024)                                         # row_stride 100: not a multiple of 16
     assert L.scone_table_gather(C.byref(desc), None, 1, None, 2, None, None) == _lib.E_INVALID
+
+
+def test_bench_reference_arm_runs_on_cpu():
+    """`bench.py --impl reference` (the CPU arm) needs no GPU and prints the contract's JSON line."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "config1", "--steps", "2",
+                          "--warmup", "1"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "tokens/s" and line["value"] > 0 and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["steps"] == 2
+    # other ranks of a torchrun launch exit quietly
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--workload", "config1",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=120, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""

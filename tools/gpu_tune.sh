@@ -1,14 +1,9 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.log
-for LF in 0 0.25 0.35; do for FMT in auto wide; do
-echo "== config2 LF=$LF fmt=$FMT"; if [ $FMT = wide ]; then export SCONE_INDEX_FORMAT=wide; else unset SCONE_INDEX_FORMAT; fi
-LF=$LF timeout 200 python tools/tune_embed.py config2 --variants=-1 2>&1 | grep -E "load_factor|lookup_only|fused|gather_only" | python -c "
-import sys,json
-for l in sys.stdin:
-    d=json.loads(l); print('  ', d if 'variant' not in d else (d['variant'], round(d['us'],2), round(d['frac'],3)))"
-done; done
-unset SCONE_INDEX_FORMAT
-echo "== config1"; timeout 200 python tools/tune_embed.py config1 --variants=-1 2>&1 | grep -E "load_factor|lookup_only|fused|gather_only" | python -c "
-import sys,json
-for l in sys.stdin:
-    d=json.loads(l); print('  ', d if 'variant' not in d else (d['variant'], round(d['us'],2), round(d['frac'],3)))"
+timeout 600 python bench.py > gpurun_out/bench_config2.json 2> gpurun_out/bench_config2.err; echo "bench rc=$?"; python -c "
+import json; d=json.load(open('gpurun_out/bench_config2.json')); print(d['value']/1e6, d['ms_per_step'], d['ms_per_step_repeats'], d['roofline']['frac'], d['e2e']['value']/1e6, d['config']['index_slot_bytes'])"; tail -3 gpurun_out/bench_config2.err
+timeout 600 python bench.py --id-dist zipf --no-cpu-baseline > gpurun_out/bench_config2_zipf.json 2> gpurun_out/bench_config2_zipf.err; python -c "
+import json; d=json.load(open('gpurun_out/bench_config2_zipf.json')); print('zipf', d['value']/1e6, d['ms_per_step'], d['roofline']['frac'], d['e2e']['value']/1e6)"
+timeout 600 python bench.py --workload config3 --id-dist zipf --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/bench_config3_zipf.json 2> gpurun_out/bench_config3_zipf.err; python -c "
+import json; d=json.load(open('gpurun_out/bench_config3_zipf.json')); print('config3 zipf', d['value']/1e6, d['ms_per_step'], d['roofline']['frac'])"
+timeout 600 python bench.py --workload config1 --steps 50 --warmup 5 --no-cpu-baseline > gpurun_out/bench_config1.json 2> gpurun_out/bench_config1.err;  python -c "
+import json; d=json.load(open('gpurun_out/bench_config1.json')); print('config1', d['value']/1e6, d['ms_per_step'], d['roofline']['frac'], d['e2e']['value']/1e6)"
