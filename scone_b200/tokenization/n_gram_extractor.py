@@ -251,6 +251,9 @@ class NGramExtractor:
             dev = torch.device("cuda", torch.cuda.current_device())
         if self._index is None or self._index.device != dev:
             self._drop_index()
+            if self._tokens.shape[1] > self.max_n:
+                # the reference only ever tests n <= max_n (n_gram_extractor.py:119), so such f-grams could never match
+                raise ValueError(f"the vocabulary holds f-grams longer than max_n = {self.max_n}; raise max_n or drop them")
             toks = torch.from_numpy(self._tokens).to(dev)
             lens = torch.from_numpy(self._lens).to(dev)
             self._index = FGramIndex(toks, lens, load_factor=load_factor)

@@ -190,3 +190,22 @@ def test_bench_reference_arm_runs_on_cpu():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--workload", "config1",
                           "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=120, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_extractor_map_assignment_like_reference_load():
+    """The reference lets callers assign the three maps (its own load() does, n_gram_extractor.py:159-165)."""
+    from scone_b200 import NGramExtractor
+    ex = NGramExtractor(max_n=3, min_freq=1, max_f_grams=10)
+    ex.f_gram_to_id = {(5, 6): 1, (7,): 0, (1, 2, 3): 2}
+    assert ex.id_to_f_gram == {0: (7,), 1: (5, 6), 2: (1, 2, 3)} and ex.f_grams == {(7,), (5, 6), (1, 2, 3)}
+    t, l = ex.vocab_arrays()
+    assert t.tolist() == [[7, -1, -1], [5, 6, -1], [1, 2, 3]] and l.tolist() == [1, 2, 3] and len(ex) == 3
+    ex.id_to_f_gram = {0: (9, 9)}
+    assert ex.f_gram_to_id == {(9, 9): 0}
+    with pytest.raises(ValueError):
+        ex.f_gram_to_id = {(1,): 0, (2,): 5}          # ids must be dense
+    ex.f_gram_to_id = {(1, 2, 3, 4): 0}                # longer than max_n: can never match in the reference either
+    import torch
+    if torch.cuda.is_available():
+        with pytest.raises(ValueError, match="longer than max_n"):
+            ex.device_index()
