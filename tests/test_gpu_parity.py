@@ -644,3 +644,38 @@ def test_embed_forward_all_hits_and_all_misses():
     allmiss = torch.full((3, 40), 7, dtype=torch.long, device=DEV)
     out, fid, ml = sb.embed_forward(ix, t, base, allmiss)
     assert bool((fid == -1).all()) and bool((ml == 0).all()) and torch.equal(out, base[7].expand(3, 40, 256))
+
+
+def test_cuda_graph_replay_and_pdl_give_identical_results(monkeypatch):
+    """The hot call is asynchronous and capture-safe: K launches replayed from one CUDA graph (as bench.py times them)
+    reproduce the eager results bit for bit, also with programmatic dependent launch switched on (SCONE_PDL=1)."""
+    sb, S = _mods()
+    toks, lens = S.make_vocab_numpy(4000, 4, 500, seed=91)
+    ix = _index(toks, lens)
+    t = sb.CacheTable(4000, 1024, "int8")
+    t.store(torch.from_numpy(S.make_rows_numpy(4000, 1024, seed=92)).to(DEV))
+    base = torch.from_numpy(S.make_rows_numpy(500, 1024, seed=93)).to(DEV).to(torch.bfloat16)
+    qs = [torch.from_numpy(S.make_stream_numpy(toks, lens, 6, 500, 500, seed=94 + k)).to(DEV) for k in range(3)]
+    eager = [sb.embed_forward(ix, t, base, q) for q in qs]
+    outs = [torch.empty_like(e[0]) for e in eager]
+    ids = [torch.empty_like(e[1]) for e in eager]
+    lens_o = [torch.empty_like(e[2]) for e in eager]
+    for pdl in (False, True):
+        if pdl:
+            monkeypatch.setenv("SCONE_PDL", "1")       # read once per process by the library: only effective if not yet latched
+        stream = torch.cuda.Stream()
+        with torch.cuda.stream(stream):
+            for k, q in enumerate(qs):
+                sb.embed_forward(ix, t, base, q, out=outs[k], out_id=ids[k], out_len=lens_o[k])
+            stream.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                for rep in range(2):
+                    for k, q in enumerate(qs):
+                        sb.embed_forward(ix, t, base, q, out=outs[k], out_id=ids[k], out_len=lens_o[k])
+            for o in outs:
+                o.zero_()
+            g.replay()
+            stream.synchronize()
+        for k in range(3):
+            assert torch.equal(outs[k], eager[k][0]) and torch.equal(ids[k], eager[k][1]) and torch.equal(lens_o[k], eager[k][2])
