@@ -253,6 +253,18 @@ class EmbeddingCache:
         return embed_forward(index, self.table, self._base_emb, input_ids, self._pos_emb if add_positions else None, out,
                              self._status)
 
+    def host_pipeline(self, batch_shape, add_positions: bool = False, slots: int = 3):
+        """A :class:`scone_b200.HostPipeline` over this cache for callers whose ids arrive in pinned HOST memory
+        (the reference tokenises on the host, ``engine.py:222-233``): copies in and out overlap the kernel."""
+        from ..pipeline import HostPipeline
+        if self._base_emb is None:
+            raise RuntimeError("call set_base_embedding(wte.weight) first")
+        if self.tier == "sharded":
+            raise ValueError("host_pipeline is for the hbm / host tiers")
+        index = self.n_gram_extractor.device_index(self.device)
+        return HostPipeline(index, self.table, self._base_emb, tuple(batch_shape),
+                            pos_emb=self._pos_emb if add_positions else None, slots=slots)
+
     def publish(self) -> None:
         """Sharded tier: make this rank's rows visible to its peers (collective; call once after the last store)."""
         if self.tier == "sharded":

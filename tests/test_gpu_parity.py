@@ -584,6 +584,14 @@ def test_host_pipeline_matches_direct_call():
     B, L = 4, 160
     hb = [torch.from_numpy(S.make_stream_numpy(toks, lens, B, L, 300, seed=80 + k)).pin_memory() for k in range(7)]
     pipe = sb.HostPipeline(ix, t, base, (B, L))
+    ex = sb.NGramExtractor.from_arrays(toks, lens)
+    cache = sb.EmbeddingCache(ex, 256, quant="int8")
+    cache.cache_embeddings(list(range(3000)), torch.from_numpy(S.make_rows_numpy(3000, 256, seed=72)), verbose=False)
+    cache.set_base_embedding(base)
+    pipe2 = cache.host_pipeline((B, L))
+    r = [pipe2.submit(h) for h in hb[:2]][-1]
+    assert torch.equal(r[0], sb.embed_forward(ix, t, base, hb[0].to(DEV))[0])
+    pipe2.flush()
     got = []
     for h in hb:
         r = pipe.submit(h)
