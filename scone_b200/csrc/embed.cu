@@ -291,15 +291,15 @@ __global__ void __launch_bounds__(32 * (NM + NG), MINB) embed_kernel(const Embed
 
 struct BulkLayout {
     int ring;        // ring slots (tiles in flight per CTA)
-    int slot_bytes;  // bytes reserved per position (>= max(row_stride, 2 D), multiple of 128)
+    int slot_bytes;  // bytes reserved per position: the row (>= max(row_stride, 2 D)) [+ the position-embedding row], multiple of 128
+    int pos_off;     // offset of the position-embedding row inside a position's slot, 0 = no position add
     int smem_bytes;  // dynamic shared memory per CTA
 };
 
 template <int QUANT, int OUT>
-__device__ __forceinline__ void stream_from_smem(const EmbedParams &p, const uint8_t *srow, int32_t fid, int32_t tok, int64_t t,
-                                                 uint8_t *__restrict__ dst, int lane, uint64_t pol) {
-    const int nchunks = p.D >> 3;
-    const uint8_t *prow = p.pos ? p.pos + pos_in_row(t, p.L, p.T) * p.D * 2 : nullptr;
+__device__ __forceinline__ void stream_from_smem(const EmbedParams &p, const uint8_t *srow, const uint8_t *prow, int32_t fid,
+                                                 int32_t tok, uint8_t *__restrict__ dst, int lane, uint64_t pol) {
+    const int nchunks = p.D >> 3;  // prow: the position-embedding row, already in shared memory, or NULL
     if (fid >= 0 && !prow) {
         float rs = 1.0f;
         if (QUANT == SCONE_QUANT_INT8) rs = *reinterpret_cast<const float *>(srow + p.scale_off);
@@ -326,30 +326,38 @@ __device__ __forceinline__ void stream_from_smem(const EmbedParams &p, const uin
 #pragma unroll 4
         for (int c = lane; c < nchunks; c += 32) stg_stream_16(dst + c * 16, *reinterpret_cast<const uint4 *>(srow + c * 16), pol);
     } else {
-        for (int c = lane; c < nchunks; c += 32) {
-            float x[8];
-            if (fid >= 0) {
-                if (QUANT == SCONE_QUANT_FP16) {
-                    decode_fp16x8(*reinterpret_cast<const uint4 *>(srow + c * 16), x);
-                } else if (QUANT == SCONE_QUANT_INT8) {
-                    decode_int8x8(*reinterpret_cast<const uint2 *>(srow + c * 8), *reinterpret_cast<const float *>(srow + p.scale_off), x);
+        // position add (the matcher staged the position row next to the table row) / zero row
+        float rs = 1.0f;
+        if (QUANT == SCONE_QUANT_INT8 && fid >= 0) rs = *reinterpret_cast<const float *>(srow + p.scale_off);
+        for (int c0 = lane; c0 < nchunks; c0 += 128) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int c = c0 + 32 * u;
+                if (c >= nchunks) continue;
+                float x[8];
+                if (fid >= 0) {
+                    if (QUANT == SCONE_QUANT_FP16) {
+                        decode_fp16x8(*reinterpret_cast<const uint4 *>(srow + c * 16), x);
+                    } else if (QUANT == SCONE_QUANT_INT8) {
+                        decode_int8x8(*reinterpret_cast<const uint2 *>(srow + c * 8), rs, x);
+                    } else {
+                        const float sc = __half2float(*(reinterpret_cast<const __half *>(srow + p.scale_off) + (c >> p.group_shift)));
+                        decode_int4x8(*reinterpret_cast<const uint32_t *>(srow + c * 4), sc, x);
+                    }
+                } else if (tok >= 0) {
+                    decode16x8<OUT>(*reinterpret_cast<const uint4 *>(srow + c * 16), x);
                 } else {
-                    const float sc = __half2float(*(reinterpret_cast<const __half *>(srow + p.scale_off) + (c >> p.group_shift)));
-                    decode_int4x8(*reinterpret_cast<const uint32_t *>(srow + c * 4), sc, x);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) x[k] = 0.0f;
                 }
-            } else if (tok >= 0) {
-                decode16x8<OUT>(*reinterpret_cast<const uint4 *>(srow + c * 16), x);
-            } else {
+                if (prow) {
+                    float y[8];
+                    decode16x8<OUT>(*reinterpret_cast<const uint4 *>(prow + c * 16), y);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) x[k] = 0.0f;
+                    for (int k = 0; k < 8; ++k) x[k] = __fadd_rn(x[k], y[k]);
+                }
+                stg_stream_16(dst + c * 16, pack16x8<OUT>(x), pol);
             }
-            if (prow) {
-                float y[8];
-                decode16x8<OUT>(__ldg(reinterpret_cast<const uint4 *>(prow + c * 16)), y);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) x[k] = __fadd_rn(x[k], y[k]);
-            }
-            stg_stream_16(dst + c * 16, pack16x8<OUT>(x), pol);
         }
     }
 }
@@ -432,7 +440,10 @@ __global__ void __launch_bounds__(32 * (NM + NG), MINB) embed_bulk_kernel(const 
                     bytes = (uint32_t)p.D * 2u;
                 }
             }
-            uint32_t total = bytes;
+            // the position-embedding row rides along into the same slot (language_model.py:253-254 fused)
+            const uint8_t *src2 = nullptr;
+            if (lay.pos_off && owner) src2 = p.pos + pos_in_row(i, p.L, p.T) * p.D * 2;
+            uint32_t total = bytes + (src2 ? (uint32_t)p.D * 2u : 0u);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xFFFFFFFFu, total, o);
             mbar_wait(&empty_bar[q], (uint32_t)(((it / R) & 1) ^ 1));
@@ -440,7 +451,9 @@ __global__ void __launch_bounds__(32 * (NM + NG), MINB) embed_bulk_kernel(const 
             __syncwarp();
             if (lane == 0) mbar_arrive_expect_tx(&full_bar[q], total);
             __syncwarp();
-            if (bytes) bulk_g2s(rows_smem + (size_t)(q * G + j) * lay.slot_bytes, src, bytes, &full_bar[q], pol);
+            uint8_t *slot = rows_smem + (size_t)(q * G + j) * lay.slot_bytes;
+            if (bytes) bulk_g2s(slot, src, bytes, &full_bar[q], pol);
+            if (src2) bulk_g2s(slot + lay.pos_off, src2, (uint32_t)p.D * 2u, &full_bar[q], policy_evict_last());
         }
     } else {
         // every gather warp waits for and releases every tile, in order (see embed_kernel)
@@ -456,8 +469,8 @@ __global__ void __launch_bounds__(32 * (NM + NG), MINB) embed_bulk_kernel(const 
                 const int2 e = ring[q * G + j];
                 const int64_t t = tile * G + j;
                 if (t < p.T) {
-                    stream_from_smem<QUANT, OUT>(p, rows_smem + (size_t)(q * G + j) * lay.slot_bytes, e.x, e.y, t, p.out + t * p.D * 2, lane,
-                                                 pol);
+                    const uint8_t *slot = rows_smem + (size_t)(q * G + j) * lay.slot_bytes;
+                    stream_from_smem<QUANT, OUT>(p, slot, lay.pos_off ? slot + lay.pos_off : nullptr, e.x, e.y, p.out + t * p.D * 2, lane, pol);
                     flagged |= (e.x < 0 && e.y < 0);
                 }
             }
@@ -527,6 +540,11 @@ static int launch_ldg(EmbedParams &p, cudaStream_t stream) {
 static bool bulk_layout(const EmbedParams &p, int G, int nm, int budget_bytes, BulkLayout &lay) {
     int64_t slot = p.row_stride > 2ll * p.D ? p.row_stride : 2ll * p.D;
     slot = (slot + 127) / 128 * 128;
+    lay.pos_off = 0;
+    if (p.pos) {  // room for the position-embedding row behind the table / fallback row
+        lay.pos_off = (int)slot;
+        slot += (2ll * p.D + 127) / 128 * 128;
+    }
     const int64_t per_tile = slot * G;
     int ring = (int)((budget_bytes - bulk_header_bytes(G)) / per_tile);
     if (ring > kMaxRing) ring = kMaxRing;
@@ -559,11 +577,12 @@ static int launch_bulk(EmbedParams &p, const BulkLayout &lay, cudaStream_t strea
 //   kNarrow6  < 6 KB moved, tiny rows : 6 matcher + 4 gather warps, 3 CTAs/SM, 70 KB ring  (needs >= 6 ring slots)
 //   kNarrow4  < 6 KB moved            : 4 matcher + 4 gather warps, 3 CTAs/SM, 70 KB ring  -- matcher-hungry
 //   kWide    >= 6 KB moved            : 6 matcher + 12 gather warps, 1 CTA/SM, 200 KB ring -- store-hungry
+//   kWide3   wide rows + position row : 3 matcher + 12 gather warps, 1 CTA/SM, 200 KB ring (when six slots do not fit)
 //   kSmall   anything                 : 2 matcher + 6 gather warps, 3 CTAs/SM, 70 KB ring
 //   kLdg     rows too wide for a ring : register-load variant
 // A shape that does not fit with P lanes per position is retried with 2P, 4P (fewer positions per tile = smaller ring
 // slots) before the next shape is considered.
-enum Shape : int { kNarrow6 = 0, kNarrow4 = 1, kWide = 2, kSmall = 3, kLdg = 4 };
+enum Shape : int { kNarrow6 = 0, kNarrow4 = 1, kWide = 2, kSmall = 3, kLdg = 4, kWide3 = 5 };
 constexpr int kNoFit = 1;
 
 template <int QUANT, int OUT, int P>
@@ -592,6 +611,9 @@ static int launch(EmbedParams &p, cudaStream_t stream, int shape) {
             return kNoFit;
         case kWide:
             if (bulk_layout(p, G, 6, 200 * 1024, lay)) return launch_bulk<QUANT, OUT, P, 6, 12, 1>(p, lay, stream);
+            return kNoFit;
+        case kWide3:
+            if (bulk_layout(p, G, 3, 200 * 1024, lay)) return launch_bulk<QUANT, OUT, P, 3, 12, 1>(p, lay, stream);
             return kNoFit;
         case kSmall:
             if (bulk_layout(p, G, 2, 70 * 1024, lay)) return launch_bulk<QUANT, OUT, P, 2, 6, 3>(p, lay, stream);
@@ -625,9 +647,9 @@ static int dispatch_one(int P, EmbedParams &p, int quant, int out_dtype, cudaStr
 // P = the fewest lanes per position the vocabulary needs.
 static int dispatch(int P, EmbedParams &p, int quant, int out_dtype, cudaStream_t stream) {
     const int64_t moved = 2ll * p.D + (p.row_stride < 2ll * p.D ? p.row_stride : 2ll * p.D);
-    const int narrow[] = {kNarrow6, kNarrow4, kSmall}, wide[] = {kWide, kSmall};
+    const int narrow[] = {kNarrow6, kNarrow4, kSmall}, wide[] = {kWide, kWide3, kSmall};
     const int *order = moved >= 6144 ? wide : narrow;
-    const int n_order = moved >= 6144 ? 2 : 3;
+    const int n_order = 3;
     int rc = kNoFit;
     for (int s = 0; s < n_order && rc == kNoFit; ++s)
         for (int pp = P; pp <= 8 && rc == kNoFit; pp <<= 1) {

@@ -96,6 +96,8 @@ def main():
         os.environ["SCONE_EMBED_VARIANT"] = v
         report("fused kind:U:NM:NG:MINB:KB=" + v, graph_time(lambda k: sb.embed_forward(index, table, base, batches[k % 8], out=out, out_id=out_id, out_len=out_len)))
     os.environ.pop("SCONE_EMBED_VARIANT", None)
+    pos = S.make_base_device(L, D, torch.bfloat16, seed=5, device=dev)
+    report("fused + wpe[position] add", graph_time(lambda k: sb.embed_forward(index, table, base, batches[k % 8], pos_emb=pos, out=out, out_id=out_id, out_len=out_len)))
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(res, open("gpurun_out/tune_" + name.replace(":", "_") + ".json", "w"), indent=1)
 
