@@ -362,6 +362,21 @@ __device__ __forceinline__ void stream_from_smem(const EmbedParams &p, const uin
     }
 }
 
+#ifdef SCONE_TUNE
+// development only: nanosecond stamps of block 0 (slots 0-7) and the last block (8-15), read by tools/timeline.py
+__device__ unsigned long long g_timeline[16];
+__device__ __forceinline__ void stamp(int k) {
+    if (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_timeline[(blockIdx.x == 0 ? 0 : 8) + k] = t;
+    }
+}
+#define SCONE_STAMP(k, cond) do { if (cond) stamp(k); } while (0)
+#else
+#define SCONE_STAMP(k, cond) do { } while (0)
+#endif
+
 constexpr int kMaxRing = 16;
 // bytes of barriers + ring metadata in front of the row slots
 __host__ __device__ constexpr int bulk_header_bytes(int G) { return (2 * kMaxRing * 8 + kMaxRing * G * 8 + 127) / 128 * 128; }
@@ -389,6 +404,7 @@ __global__ void __launch_bounds__(32 * (NM + NG), MINB) embed_bulk_kernel(const 
     __syncthreads();
     // everything above overlapped the previous kernel's tail; nothing below may run before it has completed
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    SCONE_STAMP(0, threadIdx.x == 0);
 
     if (warp < NM) {
         const int j = lane / P;
@@ -416,7 +432,9 @@ __global__ void __launch_bounds__(32 * (NM + NG), MINB) embed_bulk_kernel(const 
                 }
             } else {
                 if (ntile < p.num_tiles) ntok = load_window_token<P>(p.ids, p.T, ntile * G, lane, back);
+                SCONE_STAMP(1, warp == 0 && lane == 0 && it == 0 && wtok != -12345);   // ids of the first tile have arrived
                 const WindowMatch m = match_window<P>(p.ix, wtok, p.T, p.L, base, lane, back);
+                SCONE_STAMP(2, warp == 0 && lane == 0 && it == 0 && m.fid != -12345);  // first tile resolved
                 fid = m.fid;
                 tok = own_token<P>(wtok, lane, back);
                 if ((int64_t)tok >= p.V) tok = -1;
@@ -454,7 +472,9 @@ __global__ void __launch_bounds__(32 * (NM + NG), MINB) embed_bulk_kernel(const 
             uint8_t *slot = rows_smem + (size_t)(q * G + j) * lay.slot_bytes;
             if (bytes) bulk_g2s(slot, src, bytes, &full_bar[q], pol);
             if (src2) bulk_g2s(slot + lay.pos_off, src2, (uint32_t)p.D * 2u, &full_bar[q], policy_evict_last());
+            SCONE_STAMP(3, warp == 0 && lane == 0 && it == 0);                        // first bulk copies issued
         }
+        SCONE_STAMP(7, warp == 0 && lane == 0);                                       // matcher 0 done
     } else {
         // every gather warp waits for and releases every tile, in order (see embed_kernel)
         bool flagged = false;
@@ -464,6 +484,7 @@ __global__ void __launch_bounds__(32 * (NM + NG), MINB) embed_bulk_kernel(const 
         for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++itl) {
             const int q = (int)(itl % R);
             mbar_wait(&full_bar[q], (uint32_t)((itl / R) & 1));
+            SCONE_STAMP(4, w == 0 && lane == 0 && itl == 0);                          // first rows have landed
             const int first = (int)(((int64_t)w - (itl * G) % NG + NG) % NG);
             for (int j = first; j < G; j += NG) {
                 const int2 e = ring[q * G + j];
@@ -688,6 +709,13 @@ static int fill_table(EmbedParams &p, const scone_table_desc_t *t, const char *w
 using namespace scone;
 
 extern "C" {
+
+#ifdef SCONE_TUNE
+int scone_debug_timeline(unsigned long long *out16) {
+    SCONE_CUDA(cudaMemcpyFromSymbol(out16, g_timeline, sizeof(unsigned long long) * 16));
+    return SCONE_OK;
+}
+#endif
 
 int scone_embed_forward(const scone_index_t *index, const scone_table_desc_t *table, const void *d_base_emb, int64_t base_rows,
                         const void *d_pos_emb, const int64_t *d_ids, int64_t B, int64_t L, void *d_out, int32_t out_dtype,
