@@ -200,6 +200,13 @@ def make_cache_small():
     te_rows = np.concatenate([tok_emb[int(p)].numpy() for p in te_pos]) if len(te_pos) else np.zeros((0, D), np.float32)
     fid, ml = ref_longest(ex, q)
 
+    # artefacts exactly as the reference writes them (n_gram_extractor.py:128-141, embedding_cache.py:183-203)
+    ex.save(os.path.join(HERE, "ref_extractor.npy"))
+    small = EmbeddingCache(ex, D)
+    keep = list(range(0, N, 3))
+    small.cache_embeddings(keep, rows[keep], verbose=False)
+    small.save(os.path.join(HERE, "ref_cache.npy"))
+
     np.savez_compressed(os.path.join(HERE, "cache_small.npz"), vocab_tokens=toks, vocab_lens=lens, max_n=max_n,
                         rows=rows.numpy(), pick=np.array(pick, dtype=np.int64), gathered=got, half_bits=half_bits,
                         query=np.array(q, dtype=np.int64), assembled=assembled.numpy()[0],

@@ -685,3 +685,20 @@ def test_cuda_graph_replay_and_pdl_give_identical_results(monkeypatch):
             stream.synchronize()
         for k in range(3):
             assert torch.equal(outs[k], eager[k][0]) and torch.equal(ids[k], eager[k][1]) and torch.equal(lens_o[k], eager[k][2])
+
+
+def test_reads_cache_file_written_by_the_reference():
+    """tests/golden/ref_cache.npy was written by the unmodified reference's EmbeddingCache.save (dict backend, every third id)."""
+    import os
+    from conftest import GOLDEN
+    sb, _ = _mods()
+    z = load_golden("cache_small.npz")
+    ex = sb.NGramExtractor.load(os.path.join(GOLDEN, "ref_extractor.npy"))
+    cache = sb.EmbeddingCache.load(os.path.join(GOLDEN, "ref_cache.npy"), ex)
+    N = z["rows"].shape[0]
+    keep = list(range(0, N, 3))
+    assert len(cache.embeddings) == len(keep) and 0 in cache.embeddings and 1 not in cache.embeddings
+    got = cache.get_embeddings(keep)
+    assert torch.equal(got, torch.from_numpy(z["rows"][keep]).half().float())
+    with pytest.raises(KeyError):
+        cache.get_embeddings([1])

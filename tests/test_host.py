@@ -209,3 +209,13 @@ def test_extractor_map_assignment_like_reference_load():
     if torch.cuda.is_available():
         with pytest.raises(ValueError, match="longer than max_n"):
             ex.device_index()
+
+
+def test_reads_extractor_file_written_by_the_reference():
+    """tests/golden/ref_extractor.npy was written by the unmodified reference's NGramExtractor.save."""
+    from scone_b200 import NGramExtractor
+    z = load_golden("cache_small.npz")
+    ex = NGramExtractor.load(os.path.join(ROOT, "tests", "golden", "ref_extractor.npy"))
+    t, l = ex.vocab_arrays()
+    assert ex.max_n == int(z["max_n"]) and np.array_equal(l, z["vocab_lens"])
+    assert np.array_equal(t[:, :z["vocab_tokens"].shape[1]], z["vocab_tokens"])
