@@ -381,7 +381,7 @@ def run_ours(args, w, rank, local_rank, world):
 
     pipe_value = time_pipelined()
     e2e = {"value": max(pipe_value, sync_value), "unit": "tokens/s", "h2d_bytes_per_step": T * 8, "d2h_bytes_per_step": T * 5,
-           "mode": "pipelined (scone_b200.HostPipeline, 3 slots, 2 batches in flight)" if pipe_value >= sync_value else "synchronous call per step",
+           "mode": "pipelined (scone_b200.HostPipeline, 4 slots, up to 3 batches in flight)" if pipe_value >= sync_value else "synchronous call per step",
            "pipelined": pipe_value, "synchronous": sync_value,
            "note": "ids from pinned host memory; fgram_id + match_len read back to pinned host memory every step; the embeddings "
                    "stay in HBM for the transformer, as with the reference's get_embeddings(ids, device). `synchronous` = one "

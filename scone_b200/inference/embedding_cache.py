@@ -253,7 +253,7 @@ class EmbeddingCache:
         return embed_forward(index, self.table, self._base_emb, input_ids, self._pos_emb if add_positions else None, out,
                              self._status)
 
-    def host_pipeline(self, batch_shape, add_positions: bool = False, slots: int = 3):
+    def host_pipeline(self, batch_shape, add_positions: bool = False, slots: int = 4):
         """A :class:`scone_b200.HostPipeline` over this cache for callers whose ids arrive in pinned HOST memory
         (the reference tokenises on the host, ``engine.py:222-233``): copies in and out overlap the kernel."""
         from ..pipeline import HostPipeline
