@@ -242,8 +242,14 @@ __global__ void __launch_bounds__(32 * (NM + NG), MINB) embed_kernel(const Embed
                 wtok = ntok;
             }
             mbar_wait(&empty_bar[q], (uint32_t)(((it / R) & 1) ^ 1));
-            if ((lane % P) == 0) ring[q][j] = make_int2(fid, fid == -1 ? tok : -1);
-            __syncwarp();
+            // lane 0 publishes the whole tile and then arrives: one producer thread per phase
+            const int32_t tk = fid == -1 ? tok : -1;
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const int32_t f = __shfl_sync(0xFFFFFFFFu, fid, g * P);
+                const int32_t k2 = __shfl_sync(0xFFFFFFFFu, tk, g * P);
+                if (lane == 0) ring[q][g] = make_int2(f, k2);
+            }
             if (lane == 0) mbar_arrive(&full_bar[q]);
         }
     } else {
@@ -465,8 +471,13 @@ __global__ void __launch_bounds__(32 * (NM + NG), MINB) embed_bulk_kernel(const 
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xFFFFFFFFu, total, o);
             mbar_wait(&empty_bar[q], (uint32_t)(((it / R) & 1) ^ 1));
-            if ((lane % P) == 0) ring[q * G + j] = make_int2(fid, tok);
-            __syncwarp();
+            // lane 0 publishes the whole tile and then arrives: one producer thread per phase
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const int32_t f = __shfl_sync(0xFFFFFFFFu, fid, g * P);
+                const int32_t k2 = __shfl_sync(0xFFFFFFFFu, tok, g * P);
+                if (lane == 0) ring[q * G + g] = make_int2(f, k2);
+            }
             if (lane == 0) mbar_arrive_expect_tx(&full_bar[q], total);
             __syncwarp();
             uint8_t *slot = rows_smem + (size_t)(q * G + j) * lay.slot_bytes;
