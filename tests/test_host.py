@@ -219,3 +219,19 @@ def test_reads_extractor_file_written_by_the_reference():
     t, l = ex.vocab_arrays()
     assert ex.max_n == int(z["max_n"]) and np.array_equal(l, z["vocab_lens"])
     assert np.array_equal(t[:, :z["vocab_tokens"].shape[1]], z["vocab_tokens"])
+
+
+def test_bench_byte_accounting_matches_the_survey_formula():
+    """bytes/token = 8 + slot_bytes * P + h R + (1 - h) 2D + 2D + 5, R = 2D | D + 4 | D/2 + 2 D/128."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    assert b.row_bytes_algorithmic("fp16", 768) == 1536
+    assert b.row_bytes_algorithmic("int8", 1024) == 1028
+    assert b.row_bytes_algorithmic("int4", 4096) == 2112
+    w2, w3 = b.WORKLOADS["config2"], b.WORKLOADS["config3"]
+    # with the survey's 16-byte slots and h = 1 these are exactly its table entries (3 153 and 10 397 B/token)
+    assert b.bytes_per_token(w2, 1.0, 4, slot_bytes=16) == 8 + 64 + 1028 + 2048 + 5 == 3153
+    assert b.bytes_per_token(w3, 1.0, 5, slot_bytes=16) == 8 + 80 + 2112 + 8192 + 5 == 10397
+    assert b.bytes_per_token(w2, 0.75, 3) == 8 + 96 + 0.75 * 1028 + 0.25 * 2048 + 2048 + 5
