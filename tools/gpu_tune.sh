@@ -1,2 +1,7 @@
 mkdir -p gpurun_out
-timeout 900 compute-sanitizer --tool initcheck --print-limit 12 python tools/sanitize.py > gpurun_out/sanitizer_initcheck.log 2>&1; echo "initcheck rc=$?"; grep -E "Uninit|scone|at::|ERROR SUMMARY" gpurun_out/sanitizer_initcheck.log | sort | uniq -c | sort -rn | head -20
+for A in 32 64 128; do for W in config2 config3; do
+ALIGN=$A timeout 200 python tools/tune_embed.py $W --variants=-1 2>&1 | grep -E "row_stride|fused kind|gather_only" | python -c "
+import sys,json
+for l in sys.stdin:
+    d=json.loads(l); print('$W align=$A', d if 'variant' not in d else (d['variant'][:12], round(d['us'],2), round(d['frac'],3)))"
+done; done

@@ -56,7 +56,8 @@ def main():
     lf = float(os.environ.get("LF", "0"))
     index = sb.FGramIndex(toks, lens, load_factor=lf)
     print(json.dumps({"load_factor": lf, "index_MB": index.bytes / 1e6, "max_probe": index.max_probe, "slot_bytes": index.slot_bytes}))
-    table = sb.CacheTable(N, D, w["quant"], device=dev)
+    table = sb.CacheTable(N, D, w["quant"], device=dev, align=int(os.environ.get("ALIGN", "32")))
+    print(json.dumps({"row_stride": table.row_stride}))
     S.fill_table_device(table, seed=2)
     base = S.make_base_device(V, D, torch.bfloat16, seed=3, device=dev)
     batches = [S.make_stream_device(toks, lens, B, L, V, seed=100 + k, p_plant=1.0, pick_ids=longest) for k in range(8)]
