@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SCONE_B200_VERSION 100 /* 0.1.0 */
+#define SCONE_B200_VERSION 101 /* 0.1.1 */
 
 /* error codes */
 #define SCONE_OK 0
@@ -162,6 +162,22 @@ int scone_embed_forward(const scone_index_t *index, const scone_table_desc_t *ta
                         const int64_t *d_ids, int64_t B, int64_t L,
                         void *d_out, int32_t out_dtype,
                         int32_t *d_out_id, uint8_t *d_out_len, uint32_t *d_status, void *stream);
+
+/* Same kernel, reference-CODE combine instead of Algorithm 2's replace-or-fallback: the f-gram row is ADDED to the
+ * token embedding, `combined_embeddings = base_embeddings + f_gram_embeddings` (scone/models/language_model.py:239-243),
+ * with the row of the longest f-gram ending at the position as the f-gram term (zeros where none, engine.py:238):
+ *
+ *   out[b, i, :] = base_emb[ids[b, i], :] + dequant(table[fgram_id[b, i]])   if an f-gram ends at (b, i)
+ *                = base_emb[ids[b, i], :]                                     otherwise
+ *
+ * (+ pos_emb[i] when d_pos_emb is not NULL; language_model.py:253-254).  All adds in fp32 in the reference's order
+ * (base + row) + pos, ONE rounding (RNE) to out_dtype.  A token id outside [0, base_rows) contributes a zero base row
+ * and sets SCONE_STATUS_TOKEN_OOR.  Arguments as scone_embed_forward. */
+int scone_embed_forward_additive(const scone_index_t *index, const scone_table_desc_t *table,
+                                 const void *d_base_emb, int64_t base_rows, const void *d_pos_emb,
+                                 const int64_t *d_ids, int64_t B, int64_t L,
+                                 void *d_out, int32_t out_dtype,
+                                 int32_t *d_out_id, uint8_t *d_out_len, uint32_t *d_status, void *stream);
 
 /* Second half only: ids already resolved (used by the sharded and staged tiers).
  * d_fgram_id int32 [T] (-1 = fallback to base_emb[d_ids[t]]). */

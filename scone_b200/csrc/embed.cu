@@ -49,6 +49,7 @@ struct EmbedParams {
     int32_t scale_off;
     int32_t group_shift;  // log2(group / 8): chunk index >> group_shift = group index (INT4)
     int32_t world;        // 1 = the whole table is at `rows`
+    int32_t additive;     // 1 = reference-code combine: base row + table row on a hit (language_model.py:239-243)
 };
 
 // address of table row `fid`: local, or on the peer that owns it (NVLink)
@@ -148,6 +149,7 @@ __device__ __noinline__ void stream_general(const EmbedParams &p, int32_t fid, i
     const int nchunks = p.D >> 3;
     const uint8_t *row = fid >= 0 ? row_ptr(p, fid) : nullptr;
     const uint8_t *brow = (fid < 0 && tok >= 0) ? p.base + (int64_t)tok * p.D * 2 : nullptr;
+    const uint8_t *arow = (p.additive && fid >= 0 && tok >= 0) ? p.base + (int64_t)tok * p.D * 2 : nullptr;
     const uint8_t *prow = p.pos ? p.pos + pos_in_row(t, p.L, p.T) * p.D * 2 : nullptr;
     for (int c = lane; c < nchunks; c += 32) {
         float x[8];
@@ -165,6 +167,12 @@ __device__ __noinline__ void stream_general(const EmbedParams &p, int32_t fid, i
         } else {
 #pragma unroll
             for (int k = 0; k < 8; ++k) x[k] = 0.0f;
+        }
+        if (arow) {  // wte(ids) + f-gram row
+            float y[8];
+            decode16x8<OUT>(ldg_stream_16(arow + c * 16), y);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) x[k] = __fadd_rn(y[k], x[k]);
         }
         if (prow) {
             float y[8];
@@ -224,7 +232,7 @@ __global__ void __launch_bounds__(32 * (NM + NG), MINB) embed_kernel(const Embed
                 if (i < p.T) {
                     fid = __ldg(p.fgram_in + i);
                     if (fid >= p.num_rows) fid = -2;  // caller error: zero row + status
-                    if (fid == -1) {
+                    if (fid == -1 || (p.additive && fid >= 0)) {
                         const int64_t t64 = __ldg(p.ids + i);
                         if (t64 >= 0 && t64 < p.V) tok = (int32_t)t64;
                     }
@@ -243,7 +251,7 @@ __global__ void __launch_bounds__(32 * (NM + NG), MINB) embed_kernel(const Embed
             }
             mbar_wait(&empty_bar[q], (uint32_t)(((it / R) & 1) ^ 1));
             // lane 0 publishes the whole tile and then arrives: one producer thread per phase
-            const int32_t tk = fid == -1 ? tok : -1;
+            const int32_t tk = (fid == -1 || (p.additive && fid >= 0)) ? tok : -1;  // the base row is needed
 #pragma unroll
             for (int g = 0; g < G; ++g) {
                 const int32_t f = __shfl_sync(0xFFFFFFFFu, fid, g * P);
@@ -258,7 +266,7 @@ __global__ void __launch_bounds__(32 * (NM + NG), MINB) embed_kernel(const Embed
         // for and releases EVERY tile (even one in which it owns nothing): with parity-only mbarriers this is
         // what guarantees that no waiter is ever more than one phase away from the barrier's current phase.
         bool flagged = false;
-        const bool general = p.pos != nullptr;
+        const bool general = p.pos != nullptr || p.additive;
         const uint64_t pol = policy_evict_first();
         const int w = warp - NM;
         int64_t itl = 0;
@@ -273,7 +281,7 @@ __global__ void __launch_bounds__(32 * (NM + NG), MINB) embed_kernel(const Embed
                     uint8_t *dst = p.out + t * p.D * 2;
                     if (general || (e.x < 0 && e.y < 0)) {
                         stream_general<QUANT, OUT>(p, e.x, e.y, t, dst, lane);
-                        flagged |= (e.x < 0 && e.y < 0);
+                        flagged |= e.y < 0 && (e.x < 0 || p.additive);
                     } else if (e.x >= 0) {
                         stream_hit<QUANT, OUT, U>(p, e.x, dst, lane, pol);
                     } else {
@@ -297,16 +305,17 @@ __global__ void __launch_bounds__(32 * (NM + NG), MINB) embed_kernel(const Embed
 
 struct BulkLayout {
     int ring;        // ring slots (tiles in flight per CTA)
-    int slot_bytes;  // bytes reserved per position: the row (>= max(row_stride, 2 D)) [+ the position-embedding row], multiple of 128
+    int slot_bytes;  // bytes reserved per position: the row (>= max(row_stride, 2 D)) [+ base row] [+ position row], multiple of 128
     int pos_off;     // offset of the position-embedding row inside a position's slot, 0 = no position add
+    int add_off;     // offset of the base row staged next to a HIT's table row (additive combine), 0 = replace mode
     int smem_bytes;  // dynamic shared memory per CTA
 };
 
 template <int QUANT, int OUT>
-__device__ __forceinline__ void stream_from_smem(const EmbedParams &p, const uint8_t *srow, const uint8_t *prow, int32_t fid,
-                                                 int32_t tok, uint8_t *__restrict__ dst, int lane, uint64_t pol) {
-    const int nchunks = p.D >> 3;  // prow: the position-embedding row, already in shared memory, or NULL
-    if (fid >= 0 && !prow) {
+__device__ __forceinline__ void stream_from_smem(const EmbedParams &p, const uint8_t *srow, const uint8_t *arow, const uint8_t *prow,
+                                                 int32_t fid, int32_t tok, uint8_t *__restrict__ dst, int lane, uint64_t pol) {
+    const int nchunks = p.D >> 3;  // arow / prow: base row to add to a hit / position-embedding row, in shared memory, or NULL
+    if (fid >= 0 && !prow && !arow) {
         float rs = 1.0f;
         if (QUANT == SCONE_QUANT_INT8) rs = *reinterpret_cast<const float *>(srow + p.scale_off);
 #pragma unroll 4
@@ -332,7 +341,7 @@ __device__ __forceinline__ void stream_from_smem(const EmbedParams &p, const uin
 #pragma unroll 4
         for (int c = lane; c < nchunks; c += 32) stg_stream_16(dst + c * 16, *reinterpret_cast<const uint4 *>(srow + c * 16), pol);
     } else {
-        // position add (the matcher staged the position row next to the table row) / zero row
+        // base-row add, position add (the matcher staged those rows next to the table row) / zero row
         float rs = 1.0f;
         if (QUANT == SCONE_QUANT_INT8 && fid >= 0) rs = *reinterpret_cast<const float *>(srow + p.scale_off);
         for (int c0 = lane; c0 < nchunks; c0 += 128) {
@@ -355,6 +364,12 @@ __device__ __forceinline__ void stream_from_smem(const EmbedParams &p, const uin
                 } else {
 #pragma unroll
                     for (int k = 0; k < 8; ++k) x[k] = 0.0f;
+                }
+                if (arow) {  // wte(ids) + f-gram row
+                    float y[8];
+                    decode16x8<OUT>(*reinterpret_cast<const uint4 *>(arow + c * 16), y);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) x[k] = __fadd_rn(y[k], x[k]);
                 }
                 if (prow) {
                     float y[8];
@@ -431,7 +446,7 @@ __global__ void __launch_bounds__(32 * (NM + NG), MINB) embed_bulk_kernel(const 
                 if (i < p.T) {
                     fid = __ldg(p.fgram_in + i);
                     if (fid >= p.num_rows) fid = -2;
-                    if (fid == -1) {
+                    if (fid == -1 || (p.additive && fid >= 0)) {
                         const int64_t t64 = __ldg(p.ids + i);
                         if (t64 >= 0 && t64 < p.V) tok = (int32_t)t64;
                     }
@@ -450,7 +465,7 @@ __global__ void __launch_bounds__(32 * (NM + NG), MINB) embed_bulk_kernel(const 
                 }
                 wtok = ntok;
             }
-            if (fid != -1) tok = -1;
+            if (fid != -1 && !(p.additive && fid >= 0)) tok = -1;  // additive: a hit still needs its base row
             // source of this position's bytes
             const bool owner = (lane % P) == 0 && i < p.T;
             const uint8_t *src = nullptr;
@@ -464,10 +479,13 @@ __global__ void __launch_bounds__(32 * (NM + NG), MINB) embed_bulk_kernel(const 
                     bytes = (uint32_t)p.D * 2u;
                 }
             }
+            // additive combine: the base row of a hit rides along too (language_model.py:239-243 fused)
+            const uint8_t *src3 = nullptr;
+            if (lay.add_off && owner && fid >= 0 && tok >= 0) src3 = p.base + (int64_t)tok * p.D * 2;
             // the position-embedding row rides along into the same slot (language_model.py:253-254 fused)
             const uint8_t *src2 = nullptr;
             if (lay.pos_off && owner) src2 = p.pos + pos_in_row(i, p.L, p.T) * p.D * 2;
-            uint32_t total = bytes + (src2 ? (uint32_t)p.D * 2u : 0u);
+            uint32_t total = bytes + (src2 ? (uint32_t)p.D * 2u : 0u) + (src3 ? (uint32_t)p.D * 2u : 0u);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xFFFFFFFFu, total, o);
             mbar_wait(&empty_bar[q], (uint32_t)(((it / R) & 1) ^ 1));
@@ -483,6 +501,7 @@ __global__ void __launch_bounds__(32 * (NM + NG), MINB) embed_bulk_kernel(const 
             uint8_t *slot = rows_smem + (size_t)(q * G + j) * lay.slot_bytes;
             if (bytes) bulk_g2s(slot, src, bytes, &full_bar[q], pol);
             if (src2) bulk_g2s(slot + lay.pos_off, src2, (uint32_t)p.D * 2u, &full_bar[q], policy_evict_last());
+            if (src3) bulk_g2s(slot + lay.add_off, src3, (uint32_t)p.D * 2u, &full_bar[q], pol);
             SCONE_STAMP(3, warp == 0 && lane == 0 && it == 0);                        // first bulk copies issued
         }
         SCONE_STAMP(7, warp == 0 && lane == 0);                                       // matcher 0 done
@@ -502,8 +521,10 @@ __global__ void __launch_bounds__(32 * (NM + NG), MINB) embed_bulk_kernel(const 
                 const int64_t t = tile * G + j;
                 if (t < p.T) {
                     const uint8_t *slot = rows_smem + (size_t)(q * G + j) * lay.slot_bytes;
-                    stream_from_smem<QUANT, OUT>(p, slot, lay.pos_off ? slot + lay.pos_off : nullptr, e.x, e.y, p.out + t * p.D * 2, lane, pol);
-                    flagged |= (e.x < 0 && e.y < 0);
+                    const uint8_t *arow = (lay.add_off && e.x >= 0 && e.y >= 0) ? slot + lay.add_off : nullptr;
+                    stream_from_smem<QUANT, OUT>(p, slot, arow, lay.pos_off ? slot + lay.pos_off : nullptr, e.x, e.y, p.out + t * p.D * 2, lane,
+                                                 pol);
+                    flagged |= e.y < 0 && (e.x < 0 || lay.add_off);
                 }
             }
             __syncwarp();
@@ -572,8 +593,12 @@ static int launch_ldg(EmbedParams &p, cudaStream_t stream) {
 static bool bulk_layout(const EmbedParams &p, int G, int nm, int budget_bytes, BulkLayout &lay) {
     int64_t slot = p.row_stride > 2ll * p.D ? p.row_stride : 2ll * p.D;
     slot = (slot + 127) / 128 * 128;
-    lay.pos_off = 0;
-    if (p.pos) {  // room for the position-embedding row behind the table / fallback row
+    lay.pos_off = lay.add_off = 0;
+    if (p.additive) {  // room for a hit's base row behind the table row
+        lay.add_off = (int)slot;
+        slot += (2ll * p.D + 127) / 128 * 128;
+    }
+    if (p.pos) {  // room for the position-embedding row behind those
         lay.pos_off = (int)slot;
         slot += (2ll * p.D + 127) / 128 * 128;
     }
@@ -728,9 +753,9 @@ int scone_debug_timeline(unsigned long long *out16) {
 }
 #endif
 
-int scone_embed_forward(const scone_index_t *index, const scone_table_desc_t *table, const void *d_base_emb, int64_t base_rows,
-                        const void *d_pos_emb, const int64_t *d_ids, int64_t B, int64_t L, void *d_out, int32_t out_dtype,
-                        int32_t *d_out_id, uint8_t *d_out_len, uint32_t *d_status, void *stream_) {
+static int embed_forward_impl(const scone_index_t *index, const scone_table_desc_t *table, const void *d_base_emb, int64_t base_rows,
+                              const void *d_pos_emb, const int64_t *d_ids, int64_t B, int64_t L, void *d_out, int32_t out_dtype,
+                              int32_t *d_out_id, uint8_t *d_out_len, uint32_t *d_status, void *stream_, int32_t additive) {
     cudaStream_t stream = (cudaStream_t)stream_;
     SCONE_REQUIRE(index && table, "scone_embed_forward: NULL index or table");
     SCONE_REQUIRE(out_dtype == SCONE_OUT_BF16 || out_dtype == SCONE_OUT_FP16, "scone_embed_forward: out_dtype must be bf16 or fp16");
@@ -760,7 +785,22 @@ int scone_embed_forward(const scone_index_t *index, const scone_table_desc_t *ta
     p.out_id = d_out_id;
     p.out_len = d_out_len;
     p.status = d_status;
+    p.additive = additive;
     return dispatch(lanes_per_position(ix->len_mask, ix->max_n), p, table->quant, out_dtype, stream);
+}
+
+int scone_embed_forward(const scone_index_t *index, const scone_table_desc_t *table, const void *d_base_emb, int64_t base_rows,
+                        const void *d_pos_emb, const int64_t *d_ids, int64_t B, int64_t L, void *d_out, int32_t out_dtype,
+                        int32_t *d_out_id, uint8_t *d_out_len, uint32_t *d_status, void *stream) {
+    return embed_forward_impl(index, table, d_base_emb, base_rows, d_pos_emb, d_ids, B, L, d_out, out_dtype, d_out_id, d_out_len, d_status,
+                              stream, 0);
+}
+
+int scone_embed_forward_additive(const scone_index_t *index, const scone_table_desc_t *table, const void *d_base_emb, int64_t base_rows,
+                                 const void *d_pos_emb, const int64_t *d_ids, int64_t B, int64_t L, void *d_out, int32_t out_dtype,
+                                 int32_t *d_out_id, uint8_t *d_out_len, uint32_t *d_status, void *stream) {
+    return embed_forward_impl(index, table, d_base_emb, base_rows, d_pos_emb, d_ids, B, L, d_out, out_dtype, d_out_id, d_out_len, d_status,
+                              stream, 1);
 }
 
 int scone_embed_forward_sharded(const scone_index_t *index, const scone_table_desc_t *shard, const void *const *d_shard_rows,

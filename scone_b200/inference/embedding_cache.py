@@ -232,11 +232,13 @@ class EmbeddingCache:
         self._pos_emb = None if position_weight is None else \
             position_weight.detach().to(device=self.device, dtype=self.out_dtype).contiguous()
 
-    def lookup(self, input_ids: torch.Tensor, out: Optional[torch.Tensor] = None, add_positions: bool = False):
+    def lookup(self, input_ids: torch.Tensor, out: Optional[torch.Tensor] = None, add_positions: bool = False,
+               combine: str = "replace"):
         """``input_ids`` long [B, L] on the GPU -> (embeds [B, L, D] out_dtype, fgram_id int32 [B, L], match_len uint8 [B, L]).
 
         embeds[b, i] = dequant(row of the longest f-gram ending at i) or base_emb[input_ids[b, i]].
-        Asynchronous on the current stream.
+        ``combine="add"``: the reference code's ``wte(input_ids) + f_gram_embeddings`` (``language_model.py:239-243``)
+        instead -- the row is added to the token embedding (hbm / host tiers).  Asynchronous on the current stream.
         """
         if self._base_emb is None:
             raise RuntimeError("call set_base_embedding(wte.weight) first: misses fall back to the token embedding")
@@ -246,12 +248,14 @@ class EmbeddingCache:
         if self._status is None:
             self._status = torch.zeros((1,), dtype=torch.int32, device=self.device)
         if self.tier == "sharded":
+            if combine != "replace":
+                raise ValueError("combine='add' is not available on the sharded tier")
             from ..sharded import embed_forward_sharded
             self.table
             return embed_forward_sharded(index, self._sharded, self._base_emb, input_ids,
                                          self._pos_emb if add_positions else None, out, self._status)
         return embed_forward(index, self.table, self._base_emb, input_ids, self._pos_emb if add_positions else None, out,
-                             self._status)
+                             self._status, combine=combine)
 
     def host_pipeline(self, batch_shape, add_positions: bool = False, slots: int = 4):
         """A :class:`scone_b200.HostPipeline` over this cache for callers whose ids arrive in pinned HOST memory

@@ -113,12 +113,16 @@ class CacheTable:
 def embed_forward(index: FGramIndex, table: CacheTable, base_emb: torch.Tensor, input_ids: torch.Tensor,
                   pos_emb: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
                   status: Optional[torch.Tensor] = None, want_ids: bool = True,
-                  out_id: Optional[torch.Tensor] = None, out_len: Optional[torch.Tensor] = None):
+                  out_id: Optional[torch.Tensor] = None, out_len: Optional[torch.Tensor] = None, combine: str = "replace"):
     """The fused hot path.  Returns (embeds [B, L, D] in base_emb.dtype, fgram_id int32 [B, L], match_len uint8 [B, L]).
 
     out[b, i] = dequant(table[fgram_id[b, i]]) if an f-gram ends at (b, i) else base_emb[input_ids[b, i]]
-    (+ pos_emb[i] when given).  Everything is enqueued on the current stream; nothing synchronises.
+    (+ pos_emb[i] when given).  ``combine="add"`` is the reference code's combine instead of Algorithm 2's replacement
+    (``scone/models/language_model.py:239-243``): base_emb[input_ids[b, i]] + dequant(row) where an f-gram ends.
+    Everything is enqueued on the current stream; nothing synchronises.
     """
+    if combine not in ("replace", "add"):
+        raise ValueError("combine must be 'replace' or 'add'")
     ids = index._check_ids(input_ids)
     B, L = ids.shape
     dev = index.device
@@ -147,7 +151,8 @@ def embed_forward(index: FGramIndex, table: CacheTable, base_emb: torch.Tensor, 
     else:
         out_id = out_len = None
     with torch.cuda.device(dev):
-        _lib.check(_lib.load().scone_embed_forward(
+        entry = _lib.load().scone_embed_forward_additive if combine == "add" else _lib.load().scone_embed_forward
+        _lib.check(entry(
             index.handle, C.byref(table.desc), base_emb.data_ptr(), base_emb.shape[0],
             pos_emb.data_ptr() if pos_emb is not None else None, ids.data_ptr(), B, L, out.data_ptr(), _OUT[base_emb.dtype],
             out_id.data_ptr() if want_ids else None, out_len.data_ptr() if want_ids else None,

@@ -291,6 +291,63 @@ def test_embed_forward_with_positions():
         assert np.array_equal(_bits(out), want)
 
 
+@pytest.mark.parametrize("quant,out_dtype,D,max_n,with_pos", [
+    ("int8", "bf16", 256, 4, False), ("int8", "bf16", 1024, 4, True), ("fp16", "fp16", 768, 3, False), ("fp16", "fp16", 136, 2, True),
+    ("int4", "bf16", 4096, 5, False), ("int4", "fp16", 2048, 5, True), ("fp16", "bf16", 4096, 5, True),
+    ("fp16", "bf16", 16384, 3, True),            # too wide for a ring: register-load variant
+])
+def test_embed_forward_additive_combine(quant, out_dtype, D, max_n, with_pos):
+    """combine="add": the reference code's `base_embeddings + f_gram_embeddings` (language_model.py:239-243) fused into
+    the kernel: (fp32(wte row) + fp32(f-gram row)) [+ fp32(wpe row)], one RNE rounding; misses are the wte row."""
+    sb, S = _mods()
+    N, V, B, L = 1500, 300, 3, 131
+    toks, lens = S.make_vocab_numpy(N, max_n, V, seed=41 + D, min_n=1 if max_n < 3 else 2)
+    q = S.make_stream_numpy(toks, lens, B, L, V, seed=42, p_plant=0.6)
+    rows = S.make_rows_numpy(N, D, seed=43)
+    base_bits = po.cast_bits(S.make_rows_numpy(V, D, seed=44), out_dtype)
+    pos_bits = po.cast_bits(S.make_rows_numpy(L + 5, D, seed=45), out_dtype) if with_pos else None
+    want, wid, wlen = po.embed_forward(vocab_dict(toks, lens), max_n, po.OracleTable.from_fp32(rows, quant), base_bits, q,
+                                       out_dtype, pos_emb_bits=pos_bits, additive=True)
+    assert 0.2 < (wid >= 0).mean() < 1.0
+    ix = _index(toks, lens)
+    t = sb.CacheTable(N, D, quant)
+    t.store(torch.from_numpy(rows).to(DEV))
+    dt = TORCH_DT[out_dtype]
+    status = torch.zeros(1, dtype=torch.int32, device=DEV)
+    out, fid, ml = sb.embed_forward(ix, t, _from_bits(base_bits, dt), torch.from_numpy(q).to(DEV),
+                                    pos_emb=_from_bits(pos_bits, dt) if with_pos else None, status=status, combine="add")
+    assert np.array_equal(fid.cpu().numpy(), wid) and np.array_equal(ml.cpu().numpy(), wlen)
+    got = _bits(out)
+    assert po.ulp_distance(got, want).max() <= 1
+    assert np.array_equal(got, want)
+    assert int(status.item()) == 0
+    # replace mode on the same inputs differs exactly where an f-gram ends
+    out_r, _, _ = sb.embed_forward(ix, t, _from_bits(base_bits, dt), torch.from_numpy(q).to(DEV),
+                                   pos_emb=_from_bits(pos_bits, dt) if with_pos else None)
+    same = (_bits(out_r) == got).all(axis=-1)
+    assert same[wid < 0].all()
+    with pytest.raises(ValueError):
+        sb.embed_forward(ix, t, _from_bits(base_bits, dt), torch.from_numpy(q).to(DEV), combine="mean")
+
+
+def test_embed_forward_additive_token_outside_base_table():
+    """A hit whose own token has no base row: the f-gram row alone is written and the status bit is set."""
+    sb, S = _mods()
+    toks = np.array([[5, 60]], np.int32)
+    lens = np.array([2], np.uint8)
+    ix = _index(toks, lens)
+    t = sb.CacheTable(1, 64, "fp16")
+    rows = S.make_rows_numpy(1, 64, seed=1)
+    t.store(torch.from_numpy(rows).to(DEV))
+    base = torch.from_numpy(S.make_rows_numpy(50, 64, seed=2)).to(DEV).to(torch.float16)
+    status = torch.zeros(1, dtype=torch.int32, device=DEV)
+    q = torch.tensor([[5, 60, 7]], device=DEV)
+    out, fid, ml = sb.embed_forward(ix, t, base, q, status=status, combine="add")
+    assert fid[0].tolist() == [-1, 0, -1] and int(status.item()) == 1
+    assert torch.equal(out[0, 1], torch.from_numpy(rows[0]).half().to(DEV))
+    assert torch.equal(out[0, 0], base[5]) and torch.equal(out[0, 2], base[7])
+
+
 def test_embed_gather_resolved_ids():
     sb, S = _mods()
     r = _embed_case("int4", "fp16", 512, 5, N=1500, V=400, B=2, L=300, seed=31)
@@ -432,6 +489,13 @@ def test_input_embedding_module():
     assert emb.shape == (4, 64, 128) and emb.dtype == torch.float16 and torch.equal(fid, fid2)
     want = (plain.float() + wpe.to(DEV).half().float()[None]).half()
     assert (emb.float() - want.float()).abs().max() <= 2e-4      # single vs double rounding: <= 1 fp16 ulp at this scale
+    # combine="add": the reference code's wte + f-gram row + wpe (language_model.py:239-254), one kernel
+    mod_add = sb.SconeInputEmbedding(cache, wte, wpe, combine="add")
+    emb_add = mod_add(q)
+    rows16 = cache.table.gather(fid.clamp(min=0).reshape(-1).long(), torch.float32).reshape(4, 64, 128)
+    wte16 = wte.to(DEV).half().float()[q]
+    want_add = (wte16 + torch.where((fid >= 0)[..., None], rows16, torch.zeros_like(rows16)) + wpe.to(DEV).half().float()[None]).half()
+    assert torch.equal(emb_add, want_add)
 
 
 # ---- row-sharded tier on one GPU (world size 1 over NCCL: exercises CudaOps end to end) ------------------------------

@@ -21,7 +21,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     for name in declared:
         assert getattr(L, name) is not None
-    assert L.scone_version() == 100
+    assert L.scone_version() == 101
     assert ctypes.sizeof(_lib.TableDesc) == 40 and ctypes.sizeof(_lib.IndexInfo) == 40
 
 

@@ -223,6 +223,38 @@ def test_embed_forward_py_vs_c(quant, out_dtype):
     assert np.array_equal(cout, out)
 
 
+@pytest.mark.parametrize("out_dtype", ["bf16", "fp16"])
+def test_embed_forward_additive_is_the_reference_combine(out_dtype):
+    """additive=True restates `combined = base_embeddings + f_gram_embeddings` then `+ position_embeddings`
+    (language_model.py:239-254): checked against the same expression evaluated by torch in fp32 on the 16-bit inputs."""
+    import torch
+    z = load_golden("vocab_n5.npz")
+    g2i = vocab_dict(z["vocab_tokens"], z["vocab_lens"])
+    rng = np.random.default_rng(5)
+    N, D, V = len(g2i), 64, 300
+    q = z["query"]
+    rows = (rng.standard_normal((N, D)) * 0.02).astype(np.float32)
+    base = po.cast_bits((rng.standard_normal((V, D)) * 0.02).astype(np.float32), out_dtype)
+    pos = po.cast_bits((rng.standard_normal((q.shape[1], D)) * 0.01).astype(np.float32), out_dtype)
+    tab = po.OracleTable.from_fp32(rows, "fp16")
+    tdt = torch.bfloat16 if out_dtype == "bf16" else torch.float16
+    as_t = lambda bits: torch.from_numpy(bits.view(np.int16).copy()).view(tdt).float()
+    for with_pos in (False, True):
+        out, fid, ml = po.embed_forward(g2i, int(z["max_n"]), tab, base, q, out_dtype, pos_emb_bits=pos if with_pos else None,
+                                        additive=True)
+        assert np.array_equal(fid, z["fgram_id"])
+        fg = torch.zeros(q.shape + (D,))                                    # engine.py:238: zeros where no f-gram
+        hit = torch.from_numpy(fid >= 0)
+        fg[hit] = torch.from_numpy(tab.rows_fp32(fid[fid >= 0]))
+        combined = as_t(base)[torch.from_numpy(q)] + fg                     # language_model.py:239-243
+        if with_pos:
+            combined = combined + as_t(pos)[None]                           # language_model.py:253-254
+        want = combined.to(tdt).view(torch.int16).numpy().view(np.uint16)
+        assert np.array_equal(out, want)
+        plain, _, _ = po.embed_forward(g2i, int(z["max_n"]), tab, base, q, out_dtype, pos_emb_bits=pos if with_pos else None)
+        assert np.array_equal(plain[fid < 0], out[fid < 0])                 # misses: identical to replace mode
+
+
 # ---- property-based fuzz (SURVEY.md section 4: hypothesis over vocabularies / sequences / max_n) --------------------------
 
 from hypothesis import given, settings, strategies as st  # noqa: E402
