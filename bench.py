@@ -59,7 +59,8 @@ def row_bytes_algorithmic(quant: str, D: int, group: int = 128) -> int:
 
 
 def bytes_per_token(w, hit: float, probes: float, slot_bytes: int = 32) -> float:
-    """SURVEY.md 8d with this build's 32-byte slots: id in + probed slots + hit row / fallback row + output + (id, len) out."""
+    """id in + probed slots + hit row / fallback row + output + (id, len) out.  `slot_bytes` is the slot
+    format the index actually built (32, or 16 for the compact format; the survey's own figure is 16)."""
     D = w["D"]
     return 8 + slot_bytes * probes + hit * row_bytes_algorithmic(w["quant"], D) + (1 - hit) * 2 * D + 2 * D + 5
 
@@ -395,11 +396,11 @@ def run_ours(args, w, rank, local_rank, world):
         return
 
     # ---- roofline ---------------------------------------------------------------------------------------------
-    bpt = bytes_per_token(w, hit, probes)
+    bpt = bytes_per_token(w, hit, probes, slot_bytes=index.slot_bytes)
     peak, peak_src = measured_peak_hbm()
     achieved = bpt * T / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": "embed_kernel (fused match+gather+dequant+fallback)",
+                "traffic": None, "peak_source": peak_src, "kernel": "embed_bulk_kernel (fused match+gather+dequant+fallback)", "slot_bytes": index.slot_bytes,
                 "bytes_per_token": bpt, "hit_rate": hit, "probes_per_token": probes, "kernel_ms": kernel_ms}
     prof = os.path.join(ROOT, "profiles", f"traffic_{args.workload}.json")
     if os.path.exists(prof):

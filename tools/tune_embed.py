@@ -67,7 +67,7 @@ def main():
     sb.embed_forward(index, table, base, batches[0], out=out, out_id=out_id, out_len=out_len)
     hit = float((out_id >= 0).float().mean().item())
     probes = bin(index.len_mask).count("1")
-    bpt = bench.bytes_per_token(w, hit, probes)
+    bpt = bench.bytes_per_token(w, hit, probes, slot_bytes=index.slot_bytes)
     peak, _ = bench.measured_peak_hbm()
     res = {"workload": name, "hit": hit, "bytes_per_token": bpt, "peak": peak, "rows": []}
 
@@ -99,6 +99,8 @@ def main():
     os.environ.pop("SCONE_EMBED_VARIANT", None)
     pos = S.make_base_device(L, D, torch.bfloat16, seed=5, device=dev)
     report("fused + wpe[position] add", graph_time(lambda k: sb.embed_forward(index, table, base, batches[k % 8], pos_emb=pos, out=out, out_id=out_id, out_len=out_len)))
+    report("fused, combine=add (wte row + f-gram row)", graph_time(lambda k: sb.embed_forward(index, table, base, batches[k % 8], out=out, out_id=out_id, out_len=out_len, combine="add")))
+    report("fused, combine=add + wpe[position] add", graph_time(lambda k: sb.embed_forward(index, table, base, batches[k % 8], pos_emb=pos, out=out, out_id=out_id, out_len=out_len, combine="add")))
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(res, open("gpurun_out/tune_" + name.replace(":", "_") + ".json", "w"), indent=1)
 
