@@ -66,6 +66,7 @@ typedef struct scone_index_info {
     uint32_t len_mask;   /* bit (n-1) set when some f-gram has length n */
     int32_t max_probe;   /* longest insert probe sequence seen at build time */
     int32_t slot_bytes;  /* 32, or 16 for the compact format (all tokens < 65535 and max_n <= 6) */
+    int64_t filter_bytes; /* bytes of the L2-resident pre-filter (included in `bytes`), 0 = none */
 } scone_index_info_t;
 
 /* Where the cache rows live and how they are encoded.  Row r starts at

@@ -15,6 +15,7 @@ QUANT = {"fp16": 0, "int8": 1, "int4": 2}
 OUT_BF16, OUT_FP16, OUT_FP32 = 0, 1, 2
 STATUS_TOKEN_OOR = 1
 MAX_N = 7
+ABI_VERSION = 101        # SCONE_B200_VERSION of include/scone_b200.h this binding was written against
 
 E_INVALID, E_CUDA, E_VOCAB, E_NOMEM = -1, -2, -3, -4
 
@@ -30,7 +31,7 @@ SYMBOLS = [
 
 class IndexInfo(C.Structure):
     _fields_ = [("num_fgrams", C.c_int64), ("capacity", C.c_int64), ("bytes", C.c_int64), ("max_n", C.c_int32),
-                ("len_mask", C.c_uint32), ("max_probe", C.c_int32), ("slot_bytes", C.c_int32)]
+                ("len_mask", C.c_uint32), ("max_probe", C.c_int32), ("slot_bytes", C.c_int32), ("filter_bytes", C.c_int64)]
 
 
 class TableDesc(C.Structure):

@@ -76,6 +76,9 @@ struct scone_index_impl {
     int32_t max_probe;
     int32_t compact;
     int device;
+    uint32_t *filter;      // pre-filter words (see filter_pass), or NULL
+    uint32_t filter_mask;  // number of words - 1 (a power of two)
+    int32_t filter_always; // SCONE_INDEX_FILTER=always: consult it for every batch size (testing)
 };
 
 // device view passed by value to kernels
@@ -85,9 +88,20 @@ struct IndexView {
     uint32_t len_mask;
     int32_t max_n;
     int32_t compact;
+    const uint32_t *filter;  // NULL = probe every candidate
+    uint32_t filter_mask;
+#ifdef SCONE_TUNE
+    const uint8_t *hint;  // development only, see match.cuh
+#endif
 };
 
-inline IndexView view_of(const scone_index_impl *ix) { return IndexView{ix->slots, ix->cap, ix->len_mask, ix->max_n, ix->compact}; }
+// Batches below this many positions are latency-bound: the filter's extra L2 round trip costs more than the probes it saves.
+constexpr int64_t kFilterMinPositions = 16384;
+
+inline IndexView view_of(const scone_index_impl *ix, int64_t positions) {
+    const bool use = ix->filter && (ix->filter_always || positions >= kFilterMinPositions);
+    return IndexView{ix->slots, ix->cap, ix->len_mask, ix->max_n, ix->compact, use ? ix->filter : nullptr, ix->filter_mask};
+}
 
 // ---------------------------------------------------------------------------------------------
 // rolling 64-bit hash of the n-gram ENDING at a position: tokens are folded last-to-first, so
@@ -183,7 +197,28 @@ __device__ __forceinline__ int32_t probe16(const IndexView &ix, uint64_t h, cons
     return -1;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Pre-filter: 16 bits of a blocked Bloom filter per f-gram (two bits of one 32-bit word per key, ~1.5 % false
+// positives, no false negatives).  For vocabularies of a few million f-grams it stays resident in L2, and most candidate
+// n-grams of a position are NOT in the vocabulary: answering those from L2 instead of with a random 64-byte DRAM read of
+// a slot takes two thirds of the probe traffic (and DRAM row activations) away from the row gather they compete with.
+// The word index uses the low hash bits, the bit positions bits 32-41; the home slot comes from the top bits.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t filter_bits(uint64_t h) {
+    return (1u << (uint32_t)((h >> 32) & 31u)) | (1u << (uint32_t)((h >> 37) & 31u));
+}
+
+__device__ __forceinline__ bool filter_pass(const IndexView &ix, uint64_t h) {
+    if (!ix.filter) return true;
+    uint32_t w;
+    // (L2 default priority is enough: everything streamed is evict-first; the .L2::evict_last form exists for 256-bit loads only)
+    asm volatile("ld.global.nc.L1::evict_last.b32 %0, [%1];" : "=r"(w) : "l"(ix.filter + ((uint32_t)h & ix.filter_mask)));
+    const uint32_t b = filter_bits(h);
+    return (w & b) == b;
+}
+
 __device__ __forceinline__ int32_t probe_any(const IndexView &ix, uint64_t h, const int32_t (&key)[7]) {
+    if (!filter_pass(ix, h)) return -1;
     return ix.compact ? probe16(ix, h, key) : probe(ix, h, key);
 }
 

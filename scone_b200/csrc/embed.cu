@@ -50,6 +50,8 @@ struct EmbedParams {
     int32_t group_shift;  // log2(group / 8): chunk index >> group_shift = group index (INT4)
     int32_t world;        // 1 = the whole table is at `rows`
     int32_t additive;     // 1 = reference-code combine: base row + table row on a hit (language_model.py:239-243)
+    int32_t stagger_ns;   // matcher warp w starts its first probes w * stagger_ns later (0 = together)
+    int32_t stagger_cta_ns;  // ... and the c-th CTA of an SM (blockIdx / #SMs) another c * stagger_cta_ns later
 };
 
 // address of table row `fid`: local, or on the peer that owns it (NVLink)
@@ -435,6 +437,12 @@ __global__ void __launch_bounds__(32 * (NM + NG), MINB) embed_bulk_kernel(const 
         int64_t tile = blockIdx.x + it * gridDim.x;
         int32_t wtok = -1;
         if (!p.fgram_in && tile < p.num_tiles) wtok = load_window_token<P>(p.ids, p.T, tile * G, lane, back);
+        // The first probes of all matchers of all CTAs would hit the index as one burst of random 64-byte reads; spreading
+        // them lets the first tiles resolve (and their rows start to flow) before the burst has drained.
+        if (!p.fgram_in) {
+            const unsigned wait_ns = (unsigned)(warp * p.stagger_ns) + (unsigned)((blockIdx.x / kNumSMsB200) * p.stagger_cta_ns);
+            if (wait_ns) __nanosleep(wait_ns);
+        }
         for (; tile < p.num_tiles; it += NM, tile += (int64_t)NM * gridDim.x) {
             const int q = (int)(it % R);
             const int64_t base = tile * G;
@@ -635,42 +643,71 @@ static int launch_bulk(EmbedParams &p, const BulkLayout &lay, cudaStream_t strea
 //   kNarrow4  < 6 KB moved            : 4 matcher + 4 gather warps, 3 CTAs/SM, 70 KB ring  -- matcher-hungry
 //   kWide    >= 6 KB moved            : 6 matcher + 12 gather warps, 1 CTA/SM, 200 KB ring -- store-hungry
 //   kWide3   wide rows + position row : 3 matcher + 12 gather warps, 1 CTA/SM, 200 KB ring (when six slots do not fit)
+//   kWide2   wide rows + base + pos row: 2 matcher + 12 gather warps, 1 CTA/SM, 200 KB ring (two slots are enough)
+//   kMid     narrow rows + extra rows : 4 matcher + 8 gather warps, 2 CTAs/SM, 100 KB ring (config 2 with base row AND
+//                                       position row staged: 76-80 us against 92-95 us for kSmall)
 //   kSmall   anything                 : 2 matcher + 6 gather warps, 3 CTAs/SM, 70 KB ring
 //   kLdg     rows too wide for a ring : register-load variant
 // A shape that does not fit with P lanes per position is retried with 2P, 4P (fewer positions per tile = smaller ring
 // slots) before the next shape is considered.
-enum Shape : int { kNarrow6 = 0, kNarrow4 = 1, kWide = 2, kSmall = 3, kLdg = 4, kWide3 = 5 };
+enum Shape : int { kNarrow6 = 0, kNarrow4 = 1, kWide = 2, kSmall = 3, kLdg = 4, kWide3 = 5, kMid = 6, kWide2 = 7 };
 constexpr int kNoFit = 1;
+
+// Matcher start-up stagger (EmbedParams::stagger_ns), narrow shapes only.  Measured on config 2 (profiles/tune_r01.md):
+// 400-800 ns per matcher warp is worth 1.5 % with the pre-filter (43.3 -> 42.6 us) and 3 % without it (46.7 -> 45.3 us);
+// no effect on the wide shapes; below two tiles per matcher the delay would be exposed instead.
+template <int P, int NM, int MINB>
+static void set_stagger(EmbedParams &p) {
+    if (p.stagger_ns != 0) {  // SCONE_TUNE override; negative = off
+        if (p.stagger_ns < 0) p.stagger_ns = 0;
+        return;
+    }
+    constexpr int G = 32 / P;
+    if ((p.T + G - 1) / G >= 2ll * NM * MINB * num_sms()) p.stagger_ns = 500;
+}
 
 template <int QUANT, int OUT, int P>
 static int launch(EmbedParams &p, cudaStream_t stream, int shape) {
     constexpr int G = 32 / P;
     BulkLayout lay;
 #ifdef SCONE_TUNE
-    if constexpr (OUT == SCONE_OUT_BF16 && P == 4 && (QUANT == SCONE_QUANT_INT8 || QUANT == SCONE_QUANT_INT4)) {
+    if constexpr (OUT == SCONE_OUT_BF16 && (P == 4 || P == 8) && (QUANT == SCONE_QUANT_INT8 || QUANT == SCONE_QUANT_INT4)) {
         const Variant v = variant();
 #define SCONE_B(NMM, NGG, MM)                                                                                               \
-    if (v.kind == 1 && v.nm == NMM && v.ng == NGG && v.minb == MM && bulk_layout(p, G, NMM, v.smem_kb * 1024, lay))          \
+    if (v.kind == 1 && v.nm == NMM && v.ng == NGG && v.minb == MM && bulk_layout(p, G, NMM, v.smem_kb * 1024, lay)) \
         return launch_bulk<QUANT, OUT, P, NMM, NGG, MM>(p, lay, stream);
         SCONE_B(3, 6, 3) SCONE_B(4, 8, 2) SCONE_B(6, 6, 2) SCONE_B(8, 8, 1) SCONE_B(12, 12, 1) SCONE_B(6, 10, 2) SCONE_B(4, 12, 2)
         SCONE_B(8, 16, 1) SCONE_B(12, 20, 1) SCONE_B(3, 5, 3) SCONE_B(5, 5, 3) SCONE_B(4, 6, 3) SCONE_B(8, 12, 1) SCONE_B(6, 18, 1)
         SCONE_B(4, 12, 1) SCONE_B(8, 4, 2) SCONE_B(6, 6, 3) SCONE_B(8, 6, 2) SCONE_B(5, 3, 4) SCONE_B(6, 2, 4)
+        SCONE_B(3, 12, 1) SCONE_B(6, 12, 1) SCONE_B(6, 4, 3) SCONE_B(4, 4, 3) SCONE_B(2, 6, 3) SCONE_B(2, 12, 1)
 #undef SCONE_B
         if (v.kind == 0) return launch_ldg<QUANT, OUT, P, 4, 2, 6, 4>(p, stream);
     }
 #endif
     switch (shape) {
         case kNarrow6:
-            if (bulk_layout(p, G, 6, 70 * 1024, lay)) return launch_bulk<QUANT, OUT, P, 6, 4, 3>(p, lay, stream);
+            if (bulk_layout(p, G, 6, 70 * 1024, lay)) {
+                set_stagger<P, 6, 3>(p);
+                return launch_bulk<QUANT, OUT, P, 6, 4, 3>(p, lay, stream);
+            }
             return kNoFit;
         case kNarrow4:
-            if (bulk_layout(p, G, 4, 70 * 1024, lay)) return launch_bulk<QUANT, OUT, P, 4, 4, 3>(p, lay, stream);
+            if (bulk_layout(p, G, 4, 70 * 1024, lay)) {
+                set_stagger<P, 4, 3>(p);
+                return launch_bulk<QUANT, OUT, P, 4, 4, 3>(p, lay, stream);
+            }
             return kNoFit;
         case kWide:
             if (bulk_layout(p, G, 6, 200 * 1024, lay)) return launch_bulk<QUANT, OUT, P, 6, 12, 1>(p, lay, stream);
             return kNoFit;
         case kWide3:
             if (bulk_layout(p, G, 3, 200 * 1024, lay)) return launch_bulk<QUANT, OUT, P, 3, 12, 1>(p, lay, stream);
+            return kNoFit;
+        case kWide2:
+            if (bulk_layout(p, G, 2, 200 * 1024, lay)) return launch_bulk<QUANT, OUT, P, 2, 12, 1>(p, lay, stream);
+            return kNoFit;
+        case kMid:
+            if (bulk_layout(p, G, 4, 100 * 1024, lay)) return launch_bulk<QUANT, OUT, P, 4, 8, 2>(p, lay, stream);
             return kNoFit;
         case kSmall:
             if (bulk_layout(p, G, 2, 70 * 1024, lay)) return launch_bulk<QUANT, OUT, P, 2, 6, 3>(p, lay, stream);
@@ -704,10 +741,15 @@ static int dispatch_one(int P, EmbedParams &p, int quant, int out_dtype, cudaStr
 // P = the fewest lanes per position the vocabulary needs.
 static int dispatch(int P, EmbedParams &p, int quant, int out_dtype, cudaStream_t stream) {
     const int64_t moved = 2ll * p.D + (p.row_stride < 2ll * p.D ? p.row_stride : 2ll * p.D);
-    const int narrow[] = {kNarrow6, kNarrow4, kSmall}, wide[] = {kWide, kWide3, kSmall};
+    const int narrow[] = {kNarrow6, kNarrow4, kMid, kSmall}, wide[] = {kWide, kWide3, kWide2, kSmall};
     const int *order = moved >= 6144 ? wide : narrow;
-    const int n_order = 3;
+    const int n_order = 4;
     int rc = kNoFit;
+#ifdef SCONE_TUNE
+    if (const char *e = getenv("SCONE_EMBED_P")) P = atoi(e) > P ? atoi(e) : P;
+    if (const char *e = getenv("SCONE_STAGGER_NS")) p.stagger_ns = atoi(e);
+    if (const char *e = getenv("SCONE_STAGGER_CTA_NS")) p.stagger_cta_ns = atoi(e);
+#endif
     for (int s = 0; s < n_order && rc == kNoFit; ++s)
         for (int pp = P; pp <= 8 && rc == kNoFit; pp <<= 1) {
             rc = dispatch_one(pp, p, quant, out_dtype, stream, order[s]);
@@ -747,6 +789,16 @@ using namespace scone;
 extern "C" {
 
 #ifdef SCONE_TUNE
+static const int64_t *g_hint_ids = nullptr;
+static const uint8_t *g_hint = nullptr;
+static int64_t g_hint_n = 0;
+// what-if experiment: match lengths known in advance for the id buffer [ids_base, ids_base + n)
+int scone_debug_set_hint(const int64_t *d_ids_base, const uint8_t *d_match_len, int64_t n) {
+    g_hint_ids = d_ids_base;
+    g_hint = d_match_len;
+    g_hint_n = n;
+    return SCONE_OK;
+}
 int scone_debug_timeline(unsigned long long *out16) {
     SCONE_CUDA(cudaMemcpyFromSymbol(out16, g_timeline, sizeof(unsigned long long) * 16));
     return SCONE_OK;
@@ -773,7 +825,7 @@ static int embed_forward_impl(const scone_index_t *index, const scone_table_desc
     EmbedParams p{};
     int rc = fill_table(p, table, "scone_embed_forward");
     if (rc != SCONE_OK) return rc;
-    p.ix = view_of(ix);
+    p.ix = view_of(ix, T);
     p.fgram_in = nullptr;
     p.base = static_cast<const uint8_t *>(d_base_emb);
     p.V = base_rows;
@@ -786,6 +838,9 @@ static int embed_forward_impl(const scone_index_t *index, const scone_table_desc
     p.out_len = d_out_len;
     p.status = d_status;
     p.additive = additive;
+#ifdef SCONE_TUNE
+    if (g_hint && getenv("SCONE_HINT") && d_ids >= g_hint_ids && d_ids + T <= g_hint_ids + g_hint_n) p.ix.hint = g_hint + (d_ids - g_hint_ids);
+#endif
     return dispatch(lanes_per_position(ix->len_mask, ix->max_n), p, table->quant, out_dtype, stream);
 }
 
@@ -832,7 +887,7 @@ int scone_embed_forward_sharded(const scone_index_t *index, const scone_table_de
     p.shard_rows = reinterpret_cast<const uint8_t *const *>(d_shard_rows);
     p.rows = nullptr;
     p.num_rows = total_rows;
-    p.ix = view_of(ix);
+    p.ix = view_of(ix, T);
     p.fgram_in = nullptr;
     p.base = static_cast<const uint8_t *>(d_base_emb);
     p.V = base_rows;

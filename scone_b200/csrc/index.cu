@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(256) index_scan_kernel(const int32_t *__restri
 // word, then fill in the key.  No lookup runs concurrently with the build.
 __global__ void __launch_bounds__(256) index_build_kernel(const int32_t *__restrict__ tokens, const uint8_t *__restrict__ lens,
                                                           int64_t n, int32_t max_n, Slot *slots, uint64_t cap, int compact,
-                                                          BuildStats *stats) {
+                                                          uint32_t *filter, uint32_t filter_mask, BuildStats *stats) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int len = lens[i];
@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(256) index_build_kernel(const int32_t *__restr
     }
     if (bad) return;  // counted by the scan
     h = hash_finish(h, len);
+    if (filter) atomicOr(&filter[(uint32_t)h & filter_mask], filter_bits(h));
     int probes = 1;
     if (compact) {
         Slot16 *s16 = reinterpret_cast<Slot16 *>(slots);
@@ -215,11 +216,30 @@ int scone_index_create(const int32_t *d_tokens, const uint8_t *d_lens, int64_t n
             return e == cudaErrorMemoryAllocation ? SCONE_E_NOMEM : SCONE_E_CUDA;
         }
         SCONE_CUDA(cudaMemsetAsync(ix->slots, 0xFF, bytes, stream));
+        // pre-filter (common.cuh: filter_pass): 16 bits per f-gram, built only while it can stay in L2 (<= 16 MB, i.e.
+        // up to 8 M f-grams); SCONE_INDEX_FILTER=never / always override (testing)
+        const char *fenv = getenv("SCONE_INDEX_FILTER");
+        const bool f_never = fenv && !strcmp(fenv, "never"), f_always = fenv && !strcmp(fenv, "always");
+        if (n > 0 && !f_never && (f_always || n <= (8ll << 20))) {
+            uint64_t words = 1024;
+            while (words < (uint64_t)(n + 1) / 2) words <<= 1;
+            e = cudaMalloc(&ix->filter, words * sizeof(uint32_t));
+            if (e != cudaSuccess) {
+                set_error("scone_index_create: cudaMalloc of %llu filter bytes failed: %s", (unsigned long long)(words * 4), cudaGetErrorString(e));
+                ix->filter = nullptr;
+                return e == cudaErrorMemoryAllocation ? SCONE_E_NOMEM : SCONE_E_CUDA;
+            }
+            ix->filter_mask = (uint32_t)(words - 1);
+            ix->filter_always = f_always ? 1 : 0;
+            SCONE_CUDA(cudaMemsetAsync(ix->filter, 0, words * sizeof(uint32_t), stream));
+        }
         // pass 2: insert, then every f-gram looks itself up (duplicate audit)
         if (n > 0) {
-            index_build_kernel<<<blocks, 256, 0, stream>>>(d_tokens, d_lens, n, max_n, ix->slots, cap, ix->compact, d_stats);
+            index_build_kernel<<<blocks, 256, 0, stream>>>(d_tokens, d_lens, n, max_n, ix->slots, cap, ix->compact, ix->filter,
+                                                           ix->filter_mask, d_stats);
             SCONE_LAUNCHED();
-            IndexView v{ix->slots, cap, 0xFFFFFFFFu, max_n, ix->compact};
+            // the audit goes through the filter too: an f-gram the filter rejected would not find itself
+            IndexView v{ix->slots, cap, 0xFFFFFFFFu, max_n, ix->compact, ix->filter, ix->filter_mask};
             index_audit_kernel<<<blocks, 256, 0, stream>>>(d_tokens, d_lens, n, max_n, v, d_stats);
             SCONE_LAUNCHED();
         }
@@ -235,6 +255,7 @@ int scone_index_create(const int32_t *d_tokens, const uint8_t *d_lens, int64_t n
     }
     if (rc != SCONE_OK) {
         if (ix->slots) cudaFree(ix->slots);
+        if (ix->filter) cudaFree(ix->filter);
         delete ix;
         return rc;
     }
@@ -248,6 +269,10 @@ int scone_index_destroy(scone_index_t *index) {
     if (!index) return SCONE_OK;
     scone_index_impl *ix = reinterpret_cast<scone_index_impl *>(index);
     cudaError_t e = cudaFree(ix->slots);
+    if (ix->filter) {
+        cudaError_t e2 = cudaFree(ix->filter);
+        if (e == cudaSuccess) e = e2;
+    }
     delete ix;
     if (e != cudaSuccess) {
         set_error("scone_index_destroy: cudaFree failed: %s", cudaGetErrorString(e));
@@ -261,7 +286,8 @@ int scone_index_info(const scone_index_t *index, scone_index_info_t *info) {
     const scone_index_impl *ix = reinterpret_cast<const scone_index_impl *>(index);
     info->num_fgrams = ix->n;
     info->capacity = (int64_t)ix->cap;
-    info->bytes = (int64_t)(ix->cap * (ix->compact ? sizeof(Slot16) : sizeof(Slot)));
+    info->filter_bytes = ix->filter ? ((int64_t)ix->filter_mask + 1) * 4 : 0;
+    info->bytes = (int64_t)(ix->cap * (ix->compact ? sizeof(Slot16) : sizeof(Slot))) + info->filter_bytes;
     info->max_n = ix->max_n;
     info->len_mask = ix->len_mask;
     info->max_probe = ix->max_probe;
@@ -279,7 +305,7 @@ int scone_index_lookup(const scone_index_t *index, const int64_t *d_ids, int64_t
     SCONE_REQUIRE(d_ids, "scone_index_lookup: NULL ids");
     SCONE_REQUIRE(T < (1ll << 40), "scone_index_lookup: batch too large");
     const scone_index_impl *ix = reinterpret_cast<const scone_index_impl *>(index);
-    IndexView v = view_of(ix);
+    IndexView v = view_of(ix, T);
     const int P = lanes_per_position(ix->len_mask, ix->max_n);
     const int64_t windows = (T + (32 / P) - 1) / (32 / P);
     const unsigned blocks = (unsigned)((windows + 7) / 8);
@@ -302,7 +328,7 @@ int scone_index_match_all(const scone_index_t *index, const int64_t *d_ids, int6
     if (T == 0) return SCONE_OK;
     SCONE_REQUIRE(d_ids && d_out, "scone_index_match_all: NULL buffer");
     const scone_index_impl *ix = reinterpret_cast<const scone_index_impl *>(index);
-    IndexView v = view_of(ix);
+    IndexView v = view_of(ix, T);
     const int P = lanes_dense(ix->max_n);
     const int64_t windows = (T + (32 / P) - 1) / (32 / P);
     const unsigned blocks = (unsigned)((windows + 7) / 8);

@@ -20,12 +20,15 @@ DEV = "cuda"
 
 @pytest.fixture(autouse=True, params=["auto", "wide"])
 def index_format(request, monkeypatch):
-    """Every test runs with the automatic slot format (compact 16-byte slots whenever the tokens allow) and with the
-    32-byte format forced."""
+    """Every test runs twice: with the library defaults (compact 16-byte slots whenever the tokens allow; the Bloom
+    pre-filter consulted by large batches only), and with the 32-byte slot format forced and the pre-filter consulted
+    for every batch size."""
     if request.param == "wide":
         monkeypatch.setenv("SCONE_INDEX_FORMAT", "wide")
+        monkeypatch.setenv("SCONE_INDEX_FILTER", "always")
     else:
         monkeypatch.delenv("SCONE_INDEX_FORMAT", raising=False)
+        monkeypatch.delenv("SCONE_INDEX_FILTER", raising=False)
     return request.param
 
 
@@ -55,7 +58,7 @@ TORCH_DT = {"bf16": torch.bfloat16, "fp16": torch.float16}
 def test_library_is_native_and_loaded():
     from scone_b200 import _lib
     L = _lib.load()
-    assert L.scone_version() == 100
+    assert L.scone_version() == _lib.ABI_VERSION
     before = _lib.launch_count()
     ix = _index(np.array([[1, 2]], np.int32), np.array([2], np.uint8))
     ix.lookup(torch.tensor([[1, 2, 3]], device=DEV))
@@ -139,6 +142,30 @@ def test_lookup_edge_shapes_and_ids():
     assert fid.shape == (0, 9)
     with pytest.raises(ValueError):
         ix.lookup(torch.zeros((2, 2), dtype=torch.long))          # CPU tensor: no CPU path
+
+
+@pytest.mark.parametrize("mode", ["never", "always", None])
+def test_prefilter_never_changes_a_result(mode, monkeypatch):
+    """The Bloom pre-filter has no false negatives: with it off, on for every batch, or on by the size rule (this batch is
+    above kFilterMinPositions) the ids and lengths are the C oracle's, bit for bit."""
+    sb, S = _mods()
+    if mode is None:
+        monkeypatch.delenv("SCONE_INDEX_FILTER", raising=False)
+    else:
+        monkeypatch.setenv("SCONE_INDEX_FILTER", mode)
+    N, max_n, V, B, L = 50_000, 5, 3000, 40, 512                    # 20 480 positions
+    toks, lens = S.make_vocab_numpy(N, max_n, V, seed=71, min_n=1)
+    q = S.make_stream_numpy(toks, lens, B, L, V, seed=72, p_plant=0.5)
+    ix = _index(toks, lens)
+    assert (ix.filter_bytes == 0) == (mode == "never")
+    assert ix.filter_bytes in (0, 4 * 32768) and ix.bytes > ix.filter_bytes
+    wid, wlen = COracleIndex(toks, lens).match(q)
+    fid, ml = ix.lookup(torch.from_numpy(q).to(DEV))
+    assert np.array_equal(fid.cpu().numpy(), wid) and np.array_equal(ml.cpu().numpy(), wlen)
+    allm = ix.match_all(torch.from_numpy(q[:3]).to(DEV)).cpu().numpy()           # small batch: filter only if "always"
+    best = np.where(allm >= 0, np.arange(1, max_n + 1)[None, None, :], 0).max(axis=-1)
+    assert np.array_equal(best, wlen[:3])
+    ix.close()
 
 
 @pytest.mark.parametrize("max_n", [1, 2, 3, 4, 5, 6, 7])
