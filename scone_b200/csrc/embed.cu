@@ -404,9 +404,12 @@ constexpr int kMaxRing = 16;
 // bytes of barriers + ring metadata in front of the row slots
 __host__ __device__ constexpr int bulk_header_bytes(int G) { return (2 * kMaxRing * 8 + kMaxRing * G * 8 + 127) / 128 * 128; }
 
-template <int QUANT, int OUT, int P, int NM, int NG, int MINB>
+// ADD (compile time) = the additive combine: measured as a run-time flag it cost the plain path 1-7 % (config 1 6.56 vs
+// 6.28 us, config 2 + wpe 57.2 vs 53.1 us, config 3 1017 vs 1006 us), so the plain kernels do not carry it.
+template <int QUANT, int OUT, int P, int NM, int NG, int MINB, bool ADD>
 __global__ void __launch_bounds__(32 * (NM + NG), MINB) embed_bulk_kernel(const EmbedParams p, const BulkLayout lay) {
     constexpr int G = 32 / P;
+    const int add_off = ADD ? lay.add_off : 0;
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem);
     uint64_t *empty_bar = full_bar + kMaxRing;
@@ -454,7 +457,7 @@ __global__ void __launch_bounds__(32 * (NM + NG), MINB) embed_bulk_kernel(const 
                 if (i < p.T) {
                     fid = __ldg(p.fgram_in + i);
                     if (fid >= p.num_rows) fid = -2;
-                    if (fid == -1 || (p.additive && fid >= 0)) {
+                    if (fid == -1 || (ADD && fid >= 0)) {
                         const int64_t t64 = __ldg(p.ids + i);
                         if (t64 >= 0 && t64 < p.V) tok = (int32_t)t64;
                     }
@@ -473,7 +476,7 @@ __global__ void __launch_bounds__(32 * (NM + NG), MINB) embed_bulk_kernel(const 
                 }
                 wtok = ntok;
             }
-            if (fid != -1 && !(p.additive && fid >= 0)) tok = -1;  // additive: a hit still needs its base row
+            if (fid != -1 && !(ADD && fid >= 0)) tok = -1;  // additive: a hit still needs its base row
             // source of this position's bytes
             const bool owner = (lane % P) == 0 && i < p.T;
             const uint8_t *src = nullptr;
@@ -489,7 +492,7 @@ __global__ void __launch_bounds__(32 * (NM + NG), MINB) embed_bulk_kernel(const 
             }
             // additive combine: the base row of a hit rides along too (language_model.py:239-243 fused)
             const uint8_t *src3 = nullptr;
-            if (lay.add_off && owner && fid >= 0 && tok >= 0) src3 = p.base + (int64_t)tok * p.D * 2;
+            if (add_off && owner && fid >= 0 && tok >= 0) src3 = p.base + (int64_t)tok * p.D * 2;
             // the position-embedding row rides along into the same slot (language_model.py:253-254 fused)
             const uint8_t *src2 = nullptr;
             if (lay.pos_off && owner) src2 = p.pos + pos_in_row(i, p.L, p.T) * p.D * 2;
@@ -509,7 +512,7 @@ __global__ void __launch_bounds__(32 * (NM + NG), MINB) embed_bulk_kernel(const 
             uint8_t *slot = rows_smem + (size_t)(q * G + j) * lay.slot_bytes;
             if (bytes) bulk_g2s(slot, src, bytes, &full_bar[q], pol);
             if (src2) bulk_g2s(slot + lay.pos_off, src2, (uint32_t)p.D * 2u, &full_bar[q], policy_evict_last());
-            if (src3) bulk_g2s(slot + lay.add_off, src3, (uint32_t)p.D * 2u, &full_bar[q], pol);
+            if (src3) bulk_g2s(slot + add_off, src3, (uint32_t)p.D * 2u, &full_bar[q], pol);
             SCONE_STAMP(3, warp == 0 && lane == 0 && it == 0);                        // first bulk copies issued
         }
         SCONE_STAMP(7, warp == 0 && lane == 0);                                       // matcher 0 done
@@ -529,10 +532,10 @@ __global__ void __launch_bounds__(32 * (NM + NG), MINB) embed_bulk_kernel(const 
                 const int64_t t = tile * G + j;
                 if (t < p.T) {
                     const uint8_t *slot = rows_smem + (size_t)(q * G + j) * lay.slot_bytes;
-                    const uint8_t *arow = (lay.add_off && e.x >= 0 && e.y >= 0) ? slot + lay.add_off : nullptr;
+                    const uint8_t *arow = (add_off && e.x >= 0 && e.y >= 0) ? slot + add_off : nullptr;
                     stream_from_smem<QUANT, OUT>(p, slot, arow, lay.pos_off ? slot + lay.pos_off : nullptr, e.x, e.y, p.out + t * p.D * 2, lane,
                                                  pol);
-                    flagged |= e.y < 0 && (e.x < 0 || lay.add_off);
+                    flagged |= e.y < 0 && (e.x < 0 || add_off);
                 }
             }
             __syncwarp();
@@ -620,10 +623,10 @@ static bool bulk_layout(const EmbedParams &p, int G, int nm, int budget_bytes, B
     return true;
 }
 
-template <int QUANT, int OUT, int P, int NM, int NG, int MINB>
+template <int QUANT, int OUT, int P, int NM, int NG, int MINB, bool ADD>
 static int launch_bulk(EmbedParams &p, const BulkLayout &lay, cudaStream_t stream) {
     constexpr int G = 32 / P;
-    auto kern = embed_bulk_kernel<QUANT, OUT, P, NM, NG, MINB>;
+    auto kern = embed_bulk_kernel<QUANT, OUT, P, NM, NG, MINB, ADD>;
     static int configured[64] = {0};  // per device: the attribute lives in the device's context
     int dev = 0;
     SCONE_CUDA(cudaGetDevice(&dev));
@@ -666,7 +669,7 @@ static void set_stagger(EmbedParams &p) {
     if ((p.T + G - 1) / G >= 2ll * NM * MINB * num_sms()) p.stagger_ns = 500;
 }
 
-template <int QUANT, int OUT, int P>
+template <int QUANT, int OUT, int P, bool ADD>
 static int launch(EmbedParams &p, cudaStream_t stream, int shape) {
     constexpr int G = 32 / P;
     BulkLayout lay;
@@ -675,7 +678,7 @@ static int launch(EmbedParams &p, cudaStream_t stream, int shape) {
         const Variant v = variant();
 #define SCONE_B(NMM, NGG, MM)                                                                                               \
     if (v.kind == 1 && v.nm == NMM && v.ng == NGG && v.minb == MM && bulk_layout(p, G, NMM, v.smem_kb * 1024, lay)) \
-        return launch_bulk<QUANT, OUT, P, NMM, NGG, MM>(p, lay, stream);
+        return launch_bulk<QUANT, OUT, P, NMM, NGG, MM, ADD>(p, lay, stream);
         SCONE_B(3, 6, 3) SCONE_B(4, 8, 2) SCONE_B(6, 6, 2) SCONE_B(8, 8, 1) SCONE_B(12, 12, 1) SCONE_B(6, 10, 2) SCONE_B(4, 12, 2)
         SCONE_B(8, 16, 1) SCONE_B(12, 20, 1) SCONE_B(3, 5, 3) SCONE_B(5, 5, 3) SCONE_B(4, 6, 3) SCONE_B(8, 12, 1) SCONE_B(6, 18, 1)
         SCONE_B(4, 12, 1) SCONE_B(8, 4, 2) SCONE_B(6, 6, 3) SCONE_B(8, 6, 2) SCONE_B(5, 3, 4) SCONE_B(6, 2, 4)
@@ -688,29 +691,29 @@ static int launch(EmbedParams &p, cudaStream_t stream, int shape) {
         case kNarrow6:
             if (bulk_layout(p, G, 6, 70 * 1024, lay)) {
                 set_stagger<P, 6, 3>(p);
-                return launch_bulk<QUANT, OUT, P, 6, 4, 3>(p, lay, stream);
+                return launch_bulk<QUANT, OUT, P, 6, 4, 3, ADD>(p, lay, stream);
             }
             return kNoFit;
         case kNarrow4:
             if (bulk_layout(p, G, 4, 70 * 1024, lay)) {
                 set_stagger<P, 4, 3>(p);
-                return launch_bulk<QUANT, OUT, P, 4, 4, 3>(p, lay, stream);
+                return launch_bulk<QUANT, OUT, P, 4, 4, 3, ADD>(p, lay, stream);
             }
             return kNoFit;
         case kWide:
-            if (bulk_layout(p, G, 6, 200 * 1024, lay)) return launch_bulk<QUANT, OUT, P, 6, 12, 1>(p, lay, stream);
+            if (bulk_layout(p, G, 6, 200 * 1024, lay)) return launch_bulk<QUANT, OUT, P, 6, 12, 1, ADD>(p, lay, stream);
             return kNoFit;
         case kWide3:
-            if (bulk_layout(p, G, 3, 200 * 1024, lay)) return launch_bulk<QUANT, OUT, P, 3, 12, 1>(p, lay, stream);
+            if (bulk_layout(p, G, 3, 200 * 1024, lay)) return launch_bulk<QUANT, OUT, P, 3, 12, 1, ADD>(p, lay, stream);
             return kNoFit;
         case kWide2:
-            if (bulk_layout(p, G, 2, 200 * 1024, lay)) return launch_bulk<QUANT, OUT, P, 2, 12, 1>(p, lay, stream);
+            if (bulk_layout(p, G, 2, 200 * 1024, lay)) return launch_bulk<QUANT, OUT, P, 2, 12, 1, ADD>(p, lay, stream);
             return kNoFit;
         case kMid:
-            if (bulk_layout(p, G, 4, 100 * 1024, lay)) return launch_bulk<QUANT, OUT, P, 4, 8, 2>(p, lay, stream);
+            if (bulk_layout(p, G, 4, 100 * 1024, lay)) return launch_bulk<QUANT, OUT, P, 4, 8, 2, ADD>(p, lay, stream);
             return kNoFit;
         case kSmall:
-            if (bulk_layout(p, G, 2, 70 * 1024, lay)) return launch_bulk<QUANT, OUT, P, 2, 6, 3>(p, lay, stream);
+            if (bulk_layout(p, G, 2, 70 * 1024, lay)) return launch_bulk<QUANT, OUT, P, 2, 6, 3, ADD>(p, lay, stream);
             return kNoFit;
         default:
             return launch_ldg<QUANT, OUT, P, 4, 2, 6, 4>(p, stream);
@@ -719,11 +722,15 @@ static int launch(EmbedParams &p, cudaStream_t stream, int shape) {
 
 template <int QUANT, int OUT>
 static int launch_p(int P, EmbedParams &p, cudaStream_t stream, int shape) {
+    if (p.additive) {  // additive kernels exist for 4 and 8 lanes per position only (any P >= the vocabulary's is valid)
+        if (P <= 4) return launch<QUANT, OUT, 4, true>(p, stream, shape);
+        return launch<QUANT, OUT, 8, true>(p, stream, shape);
+    }
     switch (P) {
-        case 1: return launch<QUANT, OUT, 1>(p, stream, shape);
-        case 2: return launch<QUANT, OUT, 2>(p, stream, shape);
-        case 4: return launch<QUANT, OUT, 4>(p, stream, shape);
-        default: return launch<QUANT, OUT, 8>(p, stream, shape);
+        case 1: return launch<QUANT, OUT, 1, false>(p, stream, shape);
+        case 2: return launch<QUANT, OUT, 2, false>(p, stream, shape);
+        case 4: return launch<QUANT, OUT, 4, false>(p, stream, shape);
+        default: return launch<QUANT, OUT, 8, false>(p, stream, shape);
     }
 }
 
@@ -750,6 +757,7 @@ static int dispatch(int P, EmbedParams &p, int quant, int out_dtype, cudaStream_
     if (const char *e = getenv("SCONE_STAGGER_NS")) p.stagger_ns = atoi(e);
     if (const char *e = getenv("SCONE_STAGGER_CTA_NS")) p.stagger_cta_ns = atoi(e);
 #endif
+    if (p.additive && P < 4) P = 4;  // see launch_p
     for (int s = 0; s < n_order && rc == kNoFit; ++s)
         for (int pp = P; pp <= 8 && rc == kNoFit; pp <<= 1) {
             rc = dispatch_one(pp, p, quant, out_dtype, stream, order[s]);

@@ -2,6 +2,7 @@
 mkdir -p gpurun_out
 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/smoke.log
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.log
+timeout 300 compute-sanitizer --tool memcheck python tools/sanitize.py > gpurun_out/sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -1 gpurun_out/sanitizer_memcheck.log
 if [ "$QUICK" != "1" ]; then
 timeout 600 python bench.py > gpurun_out/bench_config2.json 2> gpurun_out/bench_config2.err; echo "bench rc=$?"; python -c "
 import json; d=json.load(open('gpurun_out/bench_config2.json')); print(d['value']/1e6, d['ms_per_step'], d['roofline']['frac'], d['e2e']['value']/1e6, d['cpu_baseline']['value'], d['gpu_launches'], d['clocks'])"; tail -3 gpurun_out/bench_config2.err

@@ -1,8 +1,10 @@
-# scratch: stagger sweep with the pre-filter on; new kMid / kWide2 shapes (SCONE_TUNE build)
+# scratch: same-box A/B -- which of this session's additions costs the plain path what (libs built with SCONE_AB_* switches)
 mkdir -p gpurun_out
-timeout 300 python tools/tune_modes.py config2 \
-  "replace;SCONE_STAGGER_NS=-1" "replace;SCONE_STAGGER_NS=200" "replace;SCONE_STAGGER_NS=300" "replace;SCONE_STAGGER_NS=400" "replace;SCONE_STAGGER_NS=500" "replace;SCONE_STAGGER_NS=600" "replace;SCONE_STAGGER_NS=800" "replace;" \
-  "pos;SCONE_STAGGER_NS=-1" "pos;" "add;SCONE_STAGGER_NS=-1" "add;" "addpos;" "addpos;SCONE_EMBED_VARIANT=1:0:2:6:3:70" \
-  > gpurun_out/tune_final_config2.log 2>&1; echo "rc=$?"; cut -c1-200 gpurun_out/tune_final_config2.log | tail -15
-timeout 300 python tools/tune_modes.py config1 "replace;" > gpurun_out/tune_final_config1.log 2>&1; echo "rc=$?"; cut -c1-200 gpurun_out/tune_final_config1.log | tail -1
-timeout 300 python tools/tune_modes.py config3 "replace;" "pos;" "add;" "addpos;" "addpos;SCONE_EMBED_P=8,SCONE_EMBED_VARIANT=1:0:3:12:1:200" > gpurun_out/tune_final_config3.log 2>&1; echo "rc=$?"; cut -c1-200 gpurun_out/tune_final_config3.log | tail -5
+for rep in 1 2; do
+for lib in "" scone_b200/lib/libscone_old.so scone_b200/lib/libscone_noadd.so scone_b200/lib/libscone_nostag.so scone_b200/lib/libscone_noboth.so; do
+AB_LIB=$lib timeout 300 python tools/tune_modes.py config1 "replace;" "replace;" 2>&1 | grep workload | cut -c1-100 | sed "s|^|lib=$lib |"
+done; done
+for lib in "" scone_b200/lib/libscone_old.so scone_b200/lib/libscone_noadd.so scone_b200/lib/libscone_noboth.so; do
+AB_LIB=$lib timeout 300 python tools/tune_modes.py config2 "replace;" "pos;" 2>&1 | grep workload | cut -c1-100 | sed "s|^|lib=$lib |"
+AB_LIB=$lib timeout 300 python tools/tune_modes.py config3 "replace;" "pos;" 2>&1 | grep workload | cut -c1-100 | sed "s|^|lib=$lib |"
+done

@@ -20,10 +20,25 @@ for quant, D, max_n, V in cases:
     pos = torch.randn(130, D, device="cuda").to(torch.bfloat16)
     out, fid, ml = sb.embed_forward(ix, t, base, q)
     outp, _, _ = sb.embed_forward(ix, t, base, q, pos_emb=pos)
+    outa, _, _ = sb.embed_forward(ix, t, base, q, combine="add")
+    outap, _, _ = sb.embed_forward(ix, t, base, q, pos_emb=pos, combine="add")
     g = sb.embed_gather(t, base, q, fid)
     m = sb.embed_mean_forward(ix, t, q)
     a = ix.match_all(q)
     torch.cuda.synchronize()
     assert torch.equal(out, g)
     print("ok", quant, D, max_n, "slot bytes", ix.slot_bytes, flush=True)
+# a batch large enough for the Bloom pre-filter and the matcher stagger (>= 16 384 positions, >= 2 tiles per matcher)
+toks, lens = S.make_vocab_numpy(20000, 4, 5000, seed=3, min_n=2)
+ix = sb.FGramIndex(torch.from_numpy(toks).cuda(), torch.from_numpy(lens).cuda())
+assert ix.filter_bytes > 0
+t = sb.CacheTable(20000, 256, "int8")
+t.store(torch.from_numpy(S.make_rows_numpy(20000, 256)).cuda())
+base = torch.randn(5000, 256, device="cuda").to(torch.bfloat16)
+q = torch.from_numpy(S.make_stream_numpy(toks, lens, 48, 1024, 5000)).cuda()
+out, fid, ml = sb.embed_forward(ix, t, base, q)
+fid2, ml2 = ix.lookup(q)
+torch.cuda.synchronize()
+assert torch.equal(fid, fid2) and torch.equal(ml, ml2) and torch.equal(out, sb.embed_gather(t, base, q, fid))
+print("ok large batch (pre-filter + stagger)", flush=True)
 print("sanitizer workload done")

@@ -22,6 +22,9 @@ KNOBS = ("SCONE_HINT", "SCONE_EMBED_VARIANT", "SCONE_EMBED_P", "SCONE_STAGGER_NS
 
 
 def main():
+    if os.environ.get("AB_LIB"):          # A/B against another build of the library (development only)
+        from scone_b200 import _lib
+        _lib.LIB_PATH = os.path.abspath(os.environ["AB_LIB"])
     name = sys.argv[1]
     w = bench.WORKLOADS[name]
     dev = torch.device("cuda", 0)
