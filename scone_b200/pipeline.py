@@ -9,9 +9,9 @@ copies of neighbouring batches overlap the kernel.  Thin wrapper over the native
 
 Each result is ``(embeds [B, L, D] on the device, fgram_id int32 [B, L] pinned host, match_len uint8 [B, L] pinned host)``
 and stays valid until the next ``submit`` (four slots by default: up to three batches in flight, one held by the caller;
-measured on config 2: 2 slots 0.70, 3 slots 1.31, 4 slots 1.36 G tokens/s).  To consume the
-embeddings on another stream, call ``torch.cuda.current_stream().synchronize()``-free code after ``submit`` returned them:
-the batch is complete (its copy-out, which follows the kernel, has been waited for).
+measured on config 2: 2 slots 0.70, 3 slots 1.31, 4 slots 1.36 G tokens/s).  A result handed back by ``submit`` /
+``flush`` is complete -- its copy-out, which follows the kernel, has been waited for -- so the embeddings can be consumed
+on any stream without further synchronisation.
 """
 
 from __future__ import annotations
