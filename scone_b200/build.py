@@ -17,14 +17,18 @@ CSRC = os.path.join(PKG, "csrc")
 LIB_DIR = os.path.join(PKG, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libscone_b200.so")
 SOURCES = ["api.cu", "index.cu", "table.cu", "embed.cu", "pipeline.cu"]
-HEADERS = ["common.cuh", "match.cuh", os.path.join("..", "..", "include", "scone_b200.h")]
+# the fused path's kernels are compiled once per (table format, output type): six translation units, in parallel
+INST_SOURCE = "embed_inst.cu"
+INSTANCES = [(q, o) for o in (0, 1) for q in (0, 1, 2)]
+HEADERS = ["common.cuh", "match.cuh", "embed_kernels.cuh", os.path.join("..", "..", "include", "scone_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
-    "-cudart", "static",
+    "-Xcompiler", "-fPIC",
+    "-Xfatbin", "-compress-all",        # -lineinfo quadruples the cubins; compressed the library is ~10 MB instead of 42 MB
 ]
+LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static"]
 
 
 def nvcc_path() -> str:
@@ -38,22 +42,39 @@ def is_stale() -> bool:
     if not os.path.exists(LIB_PATH):
         return True
     built = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    deps = [os.path.join(CSRC, s) for s in SOURCES + [INST_SOURCE] + HEADERS] + [os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > built for d in deps)
+
+
+def _run(cmd) -> str:
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+    return proc.stderr
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB_PATH
+    from concurrent.futures import ThreadPoolExecutor
     os.makedirs(LIB_DIR, exist_ok=True)
+    obj_dir = os.path.join(LIB_DIR, "obj")
+    os.makedirs(obj_dir, exist_ok=True)
+    nvcc = nvcc_path()
     tune = ["-DSCONE_TUNE"] if os.environ.get("SCONE_TUNE") else []      # extra kernel variants for tools/tune_embed.py
-    cmd = [nvcc_path()] + NVCC_FLAGS + tune + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + \
-          [os.path.join(CSRC, s) for s in SOURCES]
-    proc = subprocess.run(cmd, capture_output=True, text=True)
-    if proc.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+    common = [nvcc] + NVCC_FLAGS + tune + (["-Xptxas", "-v"] if verbose else [])
+    jobs = []
+    for q, o in INSTANCES:                                                 # the long ones first
+        obj = os.path.join(obj_dir, f"embed_inst_q{q}_{o}.o")
+        jobs.append((obj, common + [f"-DSCONE_INST_QUANT={q}", f"-DSCONE_INST_OUT={o}", "-c", os.path.join(CSRC, INST_SOURCE), "-o", obj]))
+    for src in SOURCES:
+        obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
+        jobs.append((obj, common + ["-c", os.path.join(CSRC, src), "-o", obj]))
+    with ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 1))) as pool:
+        logs = list(pool.map(lambda j: _run(j[1]), jobs))
+    _run([nvcc] + LINK_FLAGS + ["-o", LIB_PATH] + [obj for obj, _ in jobs])
     if verbose:
-        print(proc.stderr)
+        print("\n".join(logs))
     return LIB_PATH
 
 
