@@ -11,7 +11,10 @@ timeout 900 python bench.py --workload config3 --steps 20 --warmup 3 --no-cpu-ba
 import json; d=json.load(open('gpurun_out/bench_config3.json')); print('config3', d['value']/1e6, d['ms_per_step'], d['roofline']['frac'], d['e2e']['value']/1e6)"
 timeout 600 python bench.py --workload config1 --steps 50 --warmup 5 --no-cpu-baseline > gpurun_out/bench_config1.json 2> gpurun_out/bench_config1.err;  python -c "
 import json; d=json.load(open('gpurun_out/bench_config1.json')); print('config1', d['value']/1e6, d['ms_per_step'], d['roofline']['frac'], d['e2e']['value']/1e6)"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:embed -s 3 -c 1 -o gpurun_out/prof_embed_config2_r01 -f python tools/prof_embed.py config2 6 > gpurun_out/ncu_full2.log 2>&1; tail -1 gpurun_out/ncu_full2.log
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:embed -s 3 -c 1 -o gpurun_out/prof_embed_config3_r01 -f python tools/prof_embed.py config3 6 > gpurun_out/ncu_full3.log 2>&1; tail -1 gpurun_out/ncu_full3.log
+# one --set full report is ~40 MB and gpurun copies back at most 64 MiB: NCU=config2 (default) | config3 | none per call
+NCU=${NCU:-config2}
+if [ "$NCU" != "none" ]; then
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:embed -s 3 -c 1 -o gpurun_out/prof_embed_$NCU_r01 -f python tools/prof_embed.py $NCU 6 > gpurun_out/ncu_full_$NCU.log 2>&1; tail -1 gpurun_out/ncu_full_$NCU.log
+fi
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/launches_bench_config2_r01.csv python bench.py --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1; tail -1 gpurun_out/bench_under_ncu.log | cut -c1-120
 fi
