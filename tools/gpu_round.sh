@@ -14,7 +14,7 @@ import json; d=json.load(open('gpurun_out/bench_config1.json')); print('config1'
 # one --set full report is ~40 MB and gpurun copies back at most 64 MiB: NCU=config2 (default) | config3 | none per call
 NCU=${NCU:-config2}
 if [ "$NCU" != "none" ]; then
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:embed -s 3 -c 1 -o gpurun_out/prof_embed_$NCU_r01 -f python tools/prof_embed.py $NCU 6 > gpurun_out/ncu_full_$NCU.log 2>&1; tail -1 gpurun_out/ncu_full_$NCU.log
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:embed -s 3 -c 1 -o gpurun_out/prof_embed_${NCU}_r01 -f python tools/prof_embed.py $NCU 6 > gpurun_out/ncu_full_${NCU}.log 2>&1; tail -1 gpurun_out/ncu_full_${NCU}.log
 fi
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/launches_bench_config2_r01.csv python bench.py --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1; tail -1 gpurun_out/bench_under_ncu.log | cut -c1-120
 fi
