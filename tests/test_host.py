@@ -6,6 +6,7 @@ import re
 
 import numpy as np
 import pytest
+import torch
 
 from conftest import ROOT, load_golden
 from oracle import py_oracle as po
@@ -119,6 +120,15 @@ def test_tiers_and_pipeline_refuse_cpu():
     with pytest.raises(ValueError):
         sb.EmbeddingCache(sb.NGramExtractor.from_arrays(np.array([[1, 2]], np.int32), np.array([2], np.uint8)), 64, tier="nvme")
     assert sharded.shard_rows(10, 3, 4) == 2 and sharded.shard_rows(2, 3, 4) == 0
+
+
+def test_combine_argument_is_validated_before_any_device_work():
+    import scone_b200 as sb
+    from scone_b200.table import embed_forward
+    with pytest.raises(ValueError, match="combine"):
+        embed_forward(None, None, None, torch.zeros((1, 4), dtype=torch.long), combine="mean")
+    with pytest.raises(ValueError, match="combine"):
+        sb.SconeInputEmbedding(None, torch.zeros(4, 8), combine="sum")
 
 
 def test_header_cites_reference_for_every_entry_point():
