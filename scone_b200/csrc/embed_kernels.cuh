@@ -21,6 +21,10 @@
 //   * everything streamed (rows, fallback rows, output) carries an L2 evict-first policy, index slots evict-last.
 //   * every gather warp waits for and releases every tile, in order: with parity-only mbarriers no waiter may be more
 //     than one phase away from the barrier's current phase.
+//   * optional extra rows per position ride in the same ring slot: the position-embedding row (fused wpe add) and, in the
+//     additive combine (template parameter ADD), the base row of a hit.
+//
+// This header is compiled once per (table format, output type) by embed_inst.cu; embed.cu holds dispatch and the C ABI.
 #pragma once
 #include <cstdlib>
 
