@@ -122,6 +122,52 @@ def test_tiers_and_pipeline_refuse_cpu():
     assert sharded.shard_rows(10, 3, 4) == 2 and sharded.shard_rows(2, 3, 4) == 0
 
 
+def _device_hash(tokens_reversed: np.ndarray, n: int) -> np.ndarray:
+    """numpy mirror of hash_seed / hash_roll / hash_finish in scone_b200/csrc/common.cuh (uint64 arithmetic wraps)."""
+    u = np.uint64
+    h = np.full(tokens_reversed.shape[0], 0x243F6A8885A308D3, dtype=np.uint64)
+    for k in range(n):
+        h = (h ^ tokens_reversed[:, k].astype(np.uint64)) * u(0x9E3779B97F4A7C15)
+        h ^= h >> u(29)
+    h ^= u((n * 0xD6E8FEB86659FD93) & 0xFFFFFFFFFFFFFFFF)
+    h ^= h >> u(33)
+    h *= u(0xFF51AFD7ED558CCD)
+    h ^= h >> u(33)
+    h *= u(0xC4CEB9FE1A85EC53)
+    h ^= h >> u(33)
+    return h
+
+
+@pytest.mark.parametrize("n_keys", [50_000, 300_000, 1_000_000])
+def test_prefilter_parameters_give_the_documented_false_positive_rate(n_keys):
+    """The index's Bloom pre-filter (common.cuh: filter_bits / filter_pass, index.cu: sizing) restated in numpy: 16+ bits per
+    f-gram, two bits of one 32-bit word per key -> no false negatives, false positives of a few per cent at most (DESIGN.md
+    section 3 quotes ~1.5 %).  Checks the design parameters; the CUDA code itself is held to the oracle by the GPU tests."""
+    u = np.uint64
+    rng = np.random.default_rng(n_keys)
+    n = 4
+    keys = rng.integers(0, 50_257, size=(n_keys, n), dtype=np.int64)
+    probes = rng.integers(0, 50_257, size=(200_000, n), dtype=np.int64)
+    words = 1024
+    while words < (n_keys + 1) // 2:                      # scone_index_create
+        words <<= 1
+    assert 16 * n_keys <= 32 * words < 64 * n_keys + 32 * 1024
+    def word_and_bits(h):
+        w = (h & u(0xFFFFFFFF)) & u(words - 1)
+        b = (u(1) << ((h >> u(32)) & u(31))) | (u(1) << ((h >> u(37)) & u(31)))
+        return w.astype(np.int64), b.astype(np.uint32)
+    filt = np.zeros(words, dtype=np.uint32)
+    w, b = word_and_bits(_device_hash(keys, n))
+    np.bitwise_or.at(filt, w, b)
+    assert ((filt[w] & b) == b).all()                      # no false negatives
+    w2, b2 = word_and_bits(_device_hash(probes, n))
+    passed = (filt[w2] & b2) == b2
+    in_vocab = np.isin(probes.view([("", probes.dtype)] * n).ravel(), keys.view([("", keys.dtype)] * n).ravel())
+    fp = (passed & ~in_vocab).sum() / max(1, (~in_vocab).sum())
+    assert fp < 0.025, fp
+    assert len(np.unique(_device_hash(keys, n))) > 0.999 * len(np.unique(keys, axis=0))     # the 64-bit hash itself does not collide
+
+
 def test_combine_argument_is_validated_before_any_device_work():
     import scone_b200 as sb
     from scone_b200.table import embed_forward
