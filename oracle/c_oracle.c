@@ -146,6 +146,8 @@ typedef struct {
     const uint8_t *payload; int64_t row_stride;
     const uint8_t *scales; int64_t scale_stride;
     const uint16_t *base; int64_t V;
+    const uint16_t *pos;  /* optional [>= L, D] in out_dtype: the wpe term (language_model.py:253-254) */
+    int additive;         /* reference-code combine: wte row + f-gram row (language_model.py:239-243) */
     uint16_t *out;
     int64_t t0, t1; int err;
 } job;
@@ -165,6 +167,40 @@ static void longest_at(const oracle_index *ix, const int64_t *row, int64_t i, in
         if (!ok) continue;
         int32_t id = find(ix, t, n);
         if (id >= 0) { *oid = id; *olen = (uint8_t)n; return; }
+    }
+}
+
+static float widen16(const job *j, uint16_t b) {
+    if (j->out_dtype == OUT_BF16) { uint32_t u = (uint32_t)b << 16; float f; memcpy(&f, &u, 4); return f; }
+    return f16_to_f32(b);
+}
+
+static float table_elem(const job *j, const uint8_t *p, const uint8_t *sp, int d) {
+    if (j->quant == Q_FP16) { uint16_t h; memcpy(&h, p + 2 * d, 2); return f16_to_f32(h); }
+    if (j->quant == Q_INT8) { float s; memcpy(&s, sp, 4); return (float)(int8_t)p[d] * s; }
+    uint16_t h; memcpy(&h, sp + 2 * (d / j->group), 2);
+    int q = (int)((p[d >> 1] >> ((d & 1) * 4)) & 0xF) - 8;
+    return (float)q * f16_to_f32(h);
+}
+
+/* position add and/or additive combine: fp32 adds in the reference's order (wte + row) + wpe, ONE rounding
+ * (oracle/py_oracle.py embed_forward with pos_emb_bits / additive). */
+static void emit_row_general(const job *j, int32_t fid, int64_t tok, int64_t i, uint16_t *o, int *err) {
+    const int D = j->D;
+    const int tok_ok = tok >= 0 && tok < j->V;
+    const uint8_t *p = fid >= 0 ? j->payload + (int64_t)fid * j->row_stride : NULL;
+    const uint8_t *sp = (fid >= 0 && j->scales) ? j->scales + (int64_t)fid * j->scale_stride : NULL;
+    if (!tok_ok && (fid < 0 || j->additive)) *err = 1;
+    for (int d = 0; d < D; ++d) {
+        float x;
+        if (fid >= 0) {
+            x = table_elem(j, p, sp, d);
+            if (j->additive && tok_ok) x = widen16(j, j->base[tok * D + d]) + x;
+        } else {
+            x = tok_ok ? widen16(j, j->base[tok * D + d]) : 0.0f;
+        }
+        if (j->pos) x = x + widen16(j, j->pos[i * D + d]);
+        o[d] = j->out_dtype == OUT_BF16 ? f32_to_bf16(x) : f32_to_f16(x);
     }
 }
 
@@ -210,7 +246,10 @@ static void *worker(void *arg) {
         longest_at(ix, row, i, &fid, &fl);
         if (j->out_id) j->out_id[t] = fid;
         if (j->out_len) j->out_len[t] = fl;
-        if (j->do_embed) emit_row(j, fid, row[i], j->out + t * j->D, &j->err);
+        if (j->do_embed) {
+            if (j->pos || j->additive) emit_row_general(j, fid, row[i], i, j->out + t * j->D, &j->err);
+            else emit_row(j, fid, row[i], j->out + t * j->D, &j->err);
+        }
     }
     return NULL;
 }
@@ -256,5 +295,18 @@ int oracle_embed(const void *ix, int quant, int D, int group,
     j.do_embed = 1; j.quant = quant; j.D = D; j.group = group; j.out_dtype = out_dtype;
     j.payload = payload; j.row_stride = row_stride; j.scales = scales; j.scale_stride = scale_stride;
     j.base = base; j.V = V; j.out = out;
+    return run(&j, nthreads);
+}
+
+/* Same with the optional fused position add (pos: [>= L, D] in out_dtype, or NULL) and the additive combine. */
+int oracle_embed_ex(const void *ix, int quant, int D, int group,
+                    const uint8_t *payload, int64_t row_stride, const uint8_t *scales, int64_t scale_stride,
+                    const uint16_t *base, int64_t V, const uint16_t *pos, int additive, const int64_t *ids, int64_t B, int64_t L,
+                    int out_dtype, uint16_t *out, int32_t *out_id, uint8_t *out_len, int nthreads) {
+    job j; memset(&j, 0, sizeof j);
+    j.ix = (const oracle_index *)ix; j.ids = ids; j.B = B; j.L = L; j.out_id = out_id; j.out_len = out_len;
+    j.do_embed = 1; j.quant = quant; j.D = D; j.group = group; j.out_dtype = out_dtype;
+    j.payload = payload; j.row_stride = row_stride; j.scales = scales; j.scale_stride = scale_stride;
+    j.base = base; j.V = V; j.pos = pos; j.additive = additive; j.out = out;
     return run(&j, nthreads);
 }

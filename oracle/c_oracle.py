@@ -37,6 +37,10 @@ def lib():
         L.oracle_embed.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                    C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_int]
+        L.oracle_embed_ex.restype = C.c_int
+        L.oracle_embed_ex.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                      C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.oracle_f32_to_f16.restype = C.c_uint16
         L.oracle_f32_to_f16.argtypes = [C.c_float]
         L.oracle_f32_to_bf16.restype = C.c_uint16
@@ -83,8 +87,10 @@ class COracleIndex:
         return out
 
     def embed(self, quant: str, D: int, group: int, payload: np.ndarray, row_stride: int, scales, scale_stride: int,
-              base_bits: np.ndarray, ids2d: np.ndarray, out_dtype: str, nthreads: int = 1, out=None):
-        """payload / scales are raw byte views; strides in bytes.  Returns (out_bits, id, len, err)."""
+              base_bits: np.ndarray, ids2d: np.ndarray, out_dtype: str, nthreads: int = 1, out=None,
+              pos_bits: np.ndarray = None, additive: bool = False):
+        """payload / scales are raw byte views; strides in bytes.  Returns (out_bits, id, len, err).
+        ``pos_bits`` ([>= L, D] uint16 in out_dtype) / ``additive``: as py_oracle.embed_forward."""
         ids2d = np.ascontiguousarray(ids2d, dtype=np.int64)
         B, L = ids2d.shape
         base_bits = np.ascontiguousarray(base_bits, dtype=np.uint16)
@@ -92,7 +98,16 @@ class COracleIndex:
             out = np.empty((B, L, D), dtype=np.uint16)
         oid = np.empty((B, L), dtype=np.int32)
         olen = np.empty((B, L), dtype=np.uint8)
-        err = lib().oracle_embed(self.h, QUANT[quant], D, group, _p(payload), row_stride, _p(scales), scale_stride,
-                                 _p(base_bits), base_bits.shape[0], _p(ids2d), B, L, OUT[out_dtype], _p(out),
-                                 _p(oid), _p(olen), nthreads)
+        if pos_bits is None and not additive:
+            err = lib().oracle_embed(self.h, QUANT[quant], D, group, _p(payload), row_stride, _p(scales), scale_stride,
+                                     _p(base_bits), base_bits.shape[0], _p(ids2d), B, L, OUT[out_dtype], _p(out),
+                                     _p(oid), _p(olen), nthreads)
+            return out, oid, olen, err
+        if pos_bits is not None:
+            pos_bits = np.ascontiguousarray(pos_bits, dtype=np.uint16)
+            if pos_bits.shape[0] < L or pos_bits.shape[1] != D:
+                raise ValueError("pos_bits must be [>= L, D]")
+        err = lib().oracle_embed_ex(self.h, QUANT[quant], D, group, _p(payload), row_stride, _p(scales), scale_stride,
+                                    _p(base_bits), base_bits.shape[0], _p(pos_bits) if pos_bits is not None else None,
+                                    1 if additive else 0, _p(ids2d), B, L, OUT[out_dtype], _p(out), _p(oid), _p(olen), nthreads)
         return out, oid, olen, err

@@ -255,6 +255,33 @@ def test_embed_forward_additive_is_the_reference_combine(out_dtype):
         assert np.array_equal(plain[fid < 0], out[fid < 0])                 # misses: identical to replace mode
 
 
+@pytest.mark.parametrize("quant", ["fp16", "int8", "int4"])
+@pytest.mark.parametrize("out_dtype", ["bf16", "fp16"])
+@pytest.mark.parametrize("with_pos,additive", [(True, False), (False, True), (True, True)])
+def test_embed_forward_modes_py_vs_c(quant, out_dtype, with_pos, additive):
+    """The position add and the additive combine: the C restatement (used at sizes the Python one cannot reach) agrees
+    with the Python one bit for bit, including a token outside the base table (zero base row + error flag)."""
+    from scone_b200.utils.synthetic import pack_table_numpy
+    z = load_golden("vocab_n5.npz")
+    g2i = vocab_dict(z["vocab_tokens"], z["vocab_lens"])
+    rng = np.random.default_rng(17)
+    N, D, V = len(g2i), 128, 300
+    q = z["query"]
+    rows = (rng.standard_normal((N, D)) * 0.02).astype(np.float32)
+    base = po.cast_bits((rng.standard_normal((V, D)) * 0.02).astype(np.float32), out_dtype)
+    pos = po.cast_bits((rng.standard_normal((q.shape[1] + 3, D)) * 0.01).astype(np.float32), out_dtype) if with_pos else None
+    tab = po.OracleTable.from_fp32(rows, quant)
+    out, fid, ml = po.embed_forward(g2i, int(z["max_n"]), tab, base, q, out_dtype, pos_emb_bits=pos, additive=additive)
+    packed, row_stride, scale_off = pack_table_numpy(tab.quant, tab.payload, tab.scales)
+    cix = COracleIndex(z["vocab_tokens"], z["vocab_lens"])
+    scales = packed[:, scale_off:] if scale_off else None
+    cout, cid, clen, err = cix.embed(quant, D, 128, packed, row_stride, scales, row_stride, base, q, out_dtype, nthreads=3,
+                                     pos_bits=pos, additive=additive)
+    assert err == 0 and np.array_equal(cid, fid) and np.array_equal(clen, ml)
+    assert np.array_equal(cout, out)
+    assert (fid >= 0).any() and (fid < 0).any()
+
+
 # ---- property-based fuzz (SURVEY.md section 4: hypothesis over vocabularies / sequences / max_n) --------------------------
 
 from hypothesis import given, settings, strategies as st  # noqa: E402
