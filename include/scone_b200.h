@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SCONE_B200_VERSION 101 /* 0.1.1 */
+#define SCONE_B200_VERSION 200 /* 0.2.0 */
 
 /* error codes */
 #define SCONE_OK 0
@@ -44,6 +44,8 @@ extern "C" {
 #define SCONE_QUANT_FP16 0 /* row = D x fp16                       (reference: `.half()`, scone/inference/engine.py:265-266) */
 #define SCONE_QUANT_INT8 1 /* row = D x int8, then 1 x fp32 scale  (per-row symmetric) */
 #define SCONE_QUANT_INT4 2 /* row = D/2 bytes (two nibbles q+8, element 2k low), then D/group x fp16 scales */
+#define SCONE_QUANT_FP32 3 /* row = D x fp32, unquantised -- what the reference itself stores and returns
+                              (scone/inference/embedding_cache.py:84-91, :99, :111, :132-135) */
 
 /* output element types */
 #define SCONE_OUT_BF16 0
@@ -180,6 +182,28 @@ int scone_embed_forward_additive(const scone_index_t *index, const scone_table_d
                                  void *d_out, int32_t out_dtype,
                                  int32_t *d_out_id, uint8_t *d_out_len, uint32_t *d_status, void *stream);
 
+/* Options of the fused call (scone_embed_forward_ex); a NULL pointer means all defaults. */
+#define SCONE_EMBED_ADDITIVE 1u      /* the combine of scone_embed_forward_additive */
+#define SCONE_EMBED_INPUTS_STABLE 2u /* the caller vouches that NONE of this call's inputs (d_ids, the index, the table rows,
+                                        d_base_emb, d_pos_emb) is written by the kernel that precedes it on `stream`
+                                        (a serving loop: ids arrive by cudaMemcpyAsync, tables are static).  The kernel is
+                                        launched with programmatic stream serialization either way; with this flag its
+                                        matching and row fetches start under the previous kernel's tail and only its
+                                        writes wait for that kernel to complete.  Results are identical. */
+typedef struct scone_embed_opts {
+    uint32_t flags; /* SCONE_EMBED_* */
+    uint32_t reserved[3];
+} scone_embed_opts_t;
+
+/* scone_embed_forward / scone_embed_forward_additive with explicit options (same reference lines:
+ * n_gram_extractor.py:106-126, embedding_cache.py:149-181, engine.py:235-266, language_model.py:239-243). */
+int scone_embed_forward_ex(const scone_index_t *index, const scone_table_desc_t *table,
+                           const void *d_base_emb, int64_t base_rows, const void *d_pos_emb,
+                           const int64_t *d_ids, int64_t B, int64_t L,
+                           void *d_out, int32_t out_dtype,
+                           int32_t *d_out_id, uint8_t *d_out_len, uint32_t *d_status,
+                           const scone_embed_opts_t *opts, void *stream);
+
 /* Second half only: ids already resolved (used by the sharded and staged tiers).
  * d_fgram_id int32 [T] (-1 = fallback to base_emb[d_ids[t]]). */
 int scone_embed_gather(const scone_table_desc_t *table, const void *d_base_emb, int64_t base_rows,
@@ -232,8 +256,13 @@ int scone_pipeline_create(const scone_index_t *index, const scone_table_desc_t *
                           int32_t slots, void *const *d_ids_slots, void *const *d_out_slots, void *const *d_meta_slots,
                           void *const *h_meta_slots, uint32_t *d_status, scone_pipeline_t **out);
 /* Enqueue one batch from pinned host ids; *slot receives the slot it went to.  If that slot's previous batch has not
- * been waited for yet, the call waits for it first.  Returns without waiting for the new batch. */
+ * been waited for yet, the call waits for it first.  Returns without waiting for the new batch: h_ids_pinned is read by an
+ * asynchronous copy and must stay untouched until scone_pipeline_wait(slot) has returned. */
 int scone_pipeline_submit(scone_pipeline_t *p, const int64_t *h_ids_pinned, int32_t *slot);
+/* The pipeline runs on three streams of its own, ordered against the caller only at creation.  After changing anything
+ * the pipeline reads (table rows, base / position embeddings) on `stream`, call this before the next submit: every batch
+ * submitted afterwards runs behind the work already enqueued on `stream`. */
+int scone_pipeline_follow(scone_pipeline_t *p, void *stream);
 /* Block the calling host thread until the batch in `slot` is complete: its embeddings are in d_out_slots[slot] and
  * its match result in h_meta_slots[slot]. */
 int scone_pipeline_wait(scone_pipeline_t *p, int32_t slot);

@@ -134,7 +134,7 @@ uint16_t oracle_f32_to_bf16(float f) { return f32_to_bf16(f); }
 float oracle_f16_to_f32(uint16_t h) { return f16_to_f32(h); }
 
 /* ---- the path ------------------------------------------------------------ */
-enum { Q_FP16 = 0, Q_INT8 = 1, Q_INT4 = 2 };
+enum { Q_FP16 = 0, Q_INT8 = 1, Q_INT4 = 2, Q_FP32 = 3 };  /* Q_FP32: unquantised rows, embedding_cache.py:84-91,132-135 */
 enum { OUT_BF16 = 0, OUT_FP16 = 1 };
 
 typedef struct {
@@ -176,6 +176,7 @@ static float widen16(const job *j, uint16_t b) {
 }
 
 static float table_elem(const job *j, const uint8_t *p, const uint8_t *sp, int d) {
+    if (j->quant == Q_FP32) { float f; memcpy(&f, p + 4 * d, 4); return f; }
     if (j->quant == Q_FP16) { uint16_t h; memcpy(&h, p + 2 * d, 2); return f16_to_f32(h); }
     if (j->quant == Q_INT8) { float s; memcpy(&s, sp, 4); return (float)(int8_t)p[d] * s; }
     uint16_t h; memcpy(&h, sp + 2 * (d / j->group), 2);
@@ -215,7 +216,8 @@ static void emit_row(const job *j, int32_t fid, int64_t tok, uint16_t *o, int *e
     const uint8_t *sp = j->scales ? j->scales + (int64_t)fid * j->scale_stride : NULL;
     for (int d = 0; d < D; ++d) {
         float x;
-        if (j->quant == Q_FP16) { uint16_t h; memcpy(&h, p + 2 * d, 2); x = f16_to_f32(h); }
+        if (j->quant == Q_FP32) memcpy(&x, p + 4 * d, 4);
+        else if (j->quant == Q_FP16) { uint16_t h; memcpy(&h, p + 2 * d, 2); x = f16_to_f32(h); }
         else if (j->quant == Q_INT8) { float s; memcpy(&s, sp, 4); x = (float)(int8_t)p[d] * s; }
         else { uint16_t h; memcpy(&h, sp + 2 * (d / j->group), 2);
                int q = (int)((p[d >> 1] >> ((d & 1) * 4)) & 0xF) - 8; x = (float)q * f16_to_f32(h); }

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libc_oracle.so")
 _lib = None
 
-QUANT = {"fp16": 0, "int8": 1, "int4": 2}
+QUANT = {"fp16": 0, "int8": 1, "int4": 2, "fp32": 3}
 OUT = {"bf16": 0, "fp16": 1}
 
 

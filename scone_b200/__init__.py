@@ -4,7 +4,7 @@ Host code is Python/PyTorch behind the reference's ``NGramExtractor`` / ``Embedd
 hot path is hand-written CUDA reached through the C ABI of ``include/scone_b200.h``.  No CPU fallback.
 """
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"
 
 from .index import FGramIndex  # noqa: F401
 from .table import CacheTable, embed_forward, embed_gather, embed_mean_forward, table_layout  # noqa: F401

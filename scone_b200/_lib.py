@@ -11,11 +11,11 @@ import os
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "lib", "libscone_b200.so")
 
-QUANT = {"fp16": 0, "int8": 1, "int4": 2}
+QUANT = {"fp16": 0, "int8": 1, "int4": 2, "fp32": 3}
 OUT_BF16, OUT_FP16, OUT_FP32 = 0, 1, 2
 STATUS_TOKEN_OOR = 1
 MAX_N = 7
-ABI_VERSION = 101        # SCONE_B200_VERSION of include/scone_b200.h this binding was written against
+ABI_VERSION = 200        # SCONE_B200_VERSION of include/scone_b200.h this binding was written against
 
 E_INVALID, E_CUDA, E_VOCAB, E_NOMEM = -1, -2, -3, -4
 
@@ -24,8 +24,8 @@ SYMBOLS = [
     "scone_version", "scone_last_error", "scone_launch_count", "scone_host_gather_rows",
     "scone_index_create", "scone_index_destroy", "scone_index_info", "scone_index_lookup", "scone_index_match_all",
     "scone_table_layout", "scone_table_store", "scone_table_gather", "scone_table_gather_packed",
-    "scone_embed_forward", "scone_embed_forward_additive", "scone_embed_gather", "scone_embed_forward_sharded", "scone_embed_mean_forward",
-    "scone_pipeline_create", "scone_pipeline_submit", "scone_pipeline_wait", "scone_pipeline_destroy",
+    "scone_embed_forward", "scone_embed_forward_additive", "scone_embed_forward_ex", "scone_embed_gather", "scone_embed_forward_sharded", "scone_embed_mean_forward",
+    "scone_pipeline_create", "scone_pipeline_submit", "scone_pipeline_follow", "scone_pipeline_wait", "scone_pipeline_destroy",
 ]
 
 
@@ -37,6 +37,13 @@ class IndexInfo(C.Structure):
 class TableDesc(C.Structure):
     _fields_ = [("d_rows", C.c_void_p), ("row_stride", C.c_int64), ("num_rows", C.c_int64), ("quant", C.c_int32),
                 ("dim", C.c_int32), ("group", C.c_int32), ("scale_offset", C.c_int32)]
+
+
+class EmbedOpts(C.Structure):
+    _fields_ = [("flags", C.c_uint32), ("reserved", C.c_uint32 * 3)]
+
+
+EMBED_ADDITIVE, EMBED_INPUTS_STABLE = 1, 2
 
 
 class SconeError(RuntimeError):
@@ -74,10 +81,12 @@ def load() -> C.CDLL:
     L.scone_host_gather_rows.argtypes = [vp, i64, i64, vp, i64, vp, i32]
     L.scone_embed_forward.argtypes = [vp, C.POINTER(TableDesc), vp, i64, vp, vp, i64, i64, vp, i32, vp, vp, vp, vp]
     L.scone_embed_forward_additive.argtypes = L.scone_embed_forward.argtypes
+    L.scone_embed_forward_ex.argtypes = [vp, C.POINTER(TableDesc), vp, i64, vp, vp, i64, i64, vp, i32, vp, vp, vp, C.POINTER(EmbedOpts), vp]
     L.scone_embed_forward_sharded.argtypes = [vp, C.POINTER(TableDesc), vp, i32, i64, vp, i64, vp, vp, i64, i64, vp, i32, vp, vp, vp, vp]
     L.scone_embed_mean_forward.argtypes = [vp, C.POINTER(TableDesc), vp, i64, i64, vp, vp, i32, vp]
     L.scone_pipeline_create.argtypes = [vp, C.POINTER(TableDesc), vp, i64, vp, i64, i64, i32, i32, vp, vp, vp, vp, vp, C.POINTER(vp)]
     L.scone_pipeline_submit.argtypes = [vp, vp, C.POINTER(i32)]
+    L.scone_pipeline_follow.argtypes = [vp, vp]
     L.scone_pipeline_wait.argtypes = [vp, i32]
     L.scone_pipeline_destroy.argtypes = [vp]
     L.scone_embed_gather.argtypes = [C.POINTER(TableDesc), vp, i64, vp, i64, vp, vp, i64, vp, i32, vp, vp]

@@ -17,9 +17,9 @@ CSRC = os.path.join(PKG, "csrc")
 LIB_DIR = os.path.join(PKG, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libscone_b200.so")
 SOURCES = ["api.cu", "index.cu", "table.cu", "embed.cu", "pipeline.cu"]
-# the fused path's kernels are compiled once per (table format, output type): six translation units, in parallel
+# the fused path's kernels are compiled once per (table format, output type): eight translation units, in parallel
 INST_SOURCE = "embed_inst.cu"
-INSTANCES = [(q, o) for o in (0, 1) for q in (0, 1, 2)]
+INSTANCES = [(q, o) for o in (0, 1) for q in (0, 1, 2, 3)]
 HEADERS = ["common.cuh", "match.cuh", "embed_kernels.cuh", os.path.join("..", "..", "include", "scone_b200.h")]
 
 NVCC_FLAGS = [

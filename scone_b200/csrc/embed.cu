@@ -14,23 +14,28 @@ int embed_launch_q2_0(int P, EmbedParams &p, cudaStream_t stream, int shape);  /
 int embed_launch_q0_1(int P, EmbedParams &p, cudaStream_t stream, int shape);  // FP16 -> fp16
 int embed_launch_q1_1(int P, EmbedParams &p, cudaStream_t stream, int shape);  // INT8 -> fp16
 int embed_launch_q2_1(int P, EmbedParams &p, cudaStream_t stream, int shape);  // INT4 -> fp16
-static_assert(SCONE_QUANT_FP16 == 0 && SCONE_QUANT_INT8 == 1 && SCONE_QUANT_INT4 == 2 && SCONE_OUT_BF16 == 0 && SCONE_OUT_FP16 == 1,
+int embed_launch_q3_0(int P, EmbedParams &p, cudaStream_t stream, int shape);  // FP32 -> bf16
+int embed_launch_q3_1(int P, EmbedParams &p, cudaStream_t stream, int shape);  // FP32 -> fp16
+static_assert(SCONE_QUANT_FP16 == 0 && SCONE_QUANT_INT8 == 1 && SCONE_QUANT_INT4 == 2 && SCONE_QUANT_FP32 == 3 && SCONE_OUT_BF16 == 0 &&
+                  SCONE_OUT_FP16 == 1,
               "the embed_launch_q<quant>_<out> names encode these values");
 
 static int dispatch_one(int P, EmbedParams &p, int quant, int out_dtype, cudaStream_t stream, int shape) {
     if (out_dtype == SCONE_OUT_BF16) {
         if (quant == SCONE_QUANT_FP16) return embed_launch_q0_0(P, p, stream, shape);
         if (quant == SCONE_QUANT_INT8) return embed_launch_q1_0(P, p, stream, shape);
-        return embed_launch_q2_0(P, p, stream, shape);
+        if (quant == SCONE_QUANT_INT4) return embed_launch_q2_0(P, p, stream, shape);
+        return embed_launch_q3_0(P, p, stream, shape);
     }
     if (quant == SCONE_QUANT_FP16) return embed_launch_q0_1(P, p, stream, shape);
     if (quant == SCONE_QUANT_INT8) return embed_launch_q1_1(P, p, stream, shape);
-    return embed_launch_q2_1(P, p, stream, shape);
+    if (quant == SCONE_QUANT_INT4) return embed_launch_q2_1(P, p, stream, shape);
+    return embed_launch_q3_1(P, p, stream, shape);
 }
 
 // P = the fewest lanes per position the vocabulary needs.
 static int dispatch(int P, EmbedParams &p, int quant, int out_dtype, cudaStream_t stream) {
-    const int64_t moved = 2ll * p.D + (p.row_stride < 2ll * p.D ? p.row_stride : 2ll * p.D);
+    const int64_t moved = 2ll * p.D + p.row_stride;  // bytes moved per position: the stored row (or a 2 D fallback row) in, 2 D out
     const int narrow[] = {kNarrow6, kNarrow4, kMid, kSmall}, wide[] = {kWide, kWide3, kWide2, kSmall};
     const int *order = moved >= 6144 ? wide : narrow;
     const int n_order = 4;
@@ -94,7 +99,7 @@ int scone_debug_set_hint(const int64_t *d_ids_base, const uint8_t *d_match_len, 
 
 static int embed_forward_impl(const scone_index_t *index, const scone_table_desc_t *table, const void *d_base_emb, int64_t base_rows,
                               const void *d_pos_emb, const int64_t *d_ids, int64_t B, int64_t L, void *d_out, int32_t out_dtype,
-                              int32_t *d_out_id, uint8_t *d_out_len, uint32_t *d_status, void *stream_, int32_t additive) {
+                              int32_t *d_out_id, uint8_t *d_out_len, uint32_t *d_status, void *stream_, uint32_t flags) {
     cudaStream_t stream = (cudaStream_t)stream_;
     SCONE_REQUIRE(index && table, "scone_embed_forward: NULL index or table");
     SCONE_REQUIRE(out_dtype == SCONE_OUT_BF16 || out_dtype == SCONE_OUT_FP16, "scone_embed_forward: out_dtype must be bf16 or fp16");
@@ -124,7 +129,9 @@ static int embed_forward_impl(const scone_index_t *index, const scone_table_desc
     p.out_id = d_out_id;
     p.out_len = d_out_len;
     p.status = d_status;
-    p.additive = additive;
+    p.additive = (flags & SCONE_EMBED_ADDITIVE) ? 1 : 0;
+    static const bool no_early = getenv("SCONE_NO_EARLY") != nullptr;  // A/B switch: ignore SCONE_EMBED_INPUTS_STABLE
+    p.flags = no_early ? (flags & ~SCONE_EMBED_INPUTS_STABLE) : flags;
 #ifdef SCONE_TUNE
     if (g_hint && getenv("SCONE_HINT") && d_ids >= g_hint_ids && d_ids + T <= g_hint_ids + g_hint_n) p.ix.hint = g_hint + (d_ids - g_hint_ids);
 #endif
@@ -142,7 +149,16 @@ int scone_embed_forward_additive(const scone_index_t *index, const scone_table_d
                                  const void *d_pos_emb, const int64_t *d_ids, int64_t B, int64_t L, void *d_out, int32_t out_dtype,
                                  int32_t *d_out_id, uint8_t *d_out_len, uint32_t *d_status, void *stream) {
     return embed_forward_impl(index, table, d_base_emb, base_rows, d_pos_emb, d_ids, B, L, d_out, out_dtype, d_out_id, d_out_len, d_status,
-                              stream, 1);
+                              stream, SCONE_EMBED_ADDITIVE);
+}
+
+int scone_embed_forward_ex(const scone_index_t *index, const scone_table_desc_t *table, const void *d_base_emb, int64_t base_rows,
+                           const void *d_pos_emb, const int64_t *d_ids, int64_t B, int64_t L, void *d_out, int32_t out_dtype,
+                           int32_t *d_out_id, uint8_t *d_out_len, uint32_t *d_status, const scone_embed_opts_t *opts, void *stream) {
+    const uint32_t flags = opts ? opts->flags : 0u;
+    SCONE_REQUIRE((flags & ~(SCONE_EMBED_ADDITIVE | SCONE_EMBED_INPUTS_STABLE)) == 0, "scone_embed_forward_ex: unknown flag bits 0x%x", flags);
+    return embed_forward_impl(index, table, d_base_emb, base_rows, d_pos_emb, d_ids, B, L, d_out, out_dtype, d_out_id, d_out_len, d_status,
+                              stream, flags);
 }
 
 int scone_embed_forward_sharded(const scone_index_t *index, const scone_table_desc_t *shard, const void *const *d_shard_rows,

@@ -57,7 +57,14 @@ struct EmbedParams {
     int32_t additive;     // 1 = reference-code combine: base row + table row on a hit (language_model.py:239-243)
     int32_t stagger_ns;   // matcher warp w starts its first probes w * stagger_ns later (0 = together)
     int32_t stagger_cta_ns;  // ... and the c-th CTA of an SM (blockIdx / #SMs) another c * stagger_cta_ns later
+    uint32_t flags;          // SCONE_EMBED_* of scone_embed_opts_t
 };
+
+// row bytes holding 8 consecutive elements of a stored row
+template <int QUANT>
+__host__ __device__ constexpr int chunk_bytes() {
+    return QUANT == SCONE_QUANT_FP32 ? 32 : QUANT == SCONE_QUANT_FP16 ? 16 : QUANT == SCONE_QUANT_INT8 ? 8 : 4;
+}
 
 // address of table row `fid`: local, or on the peer that owns it (NVLink)
 __device__ __forceinline__ const uint8_t *row_ptr(const EmbedParams &p, int32_t fid) {
@@ -70,13 +77,16 @@ __device__ __forceinline__ const uint8_t *row_ptr(const EmbedParams &p, int32_t 
 
 constexpr int kRing = 16;  // tiles the matchers may run ahead of the gather warps
 
+// programmatic dependent launch: block until the grid this one was launched behind has completed and its writes are visible
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 template <int OUT>
-__device__ __forceinline__ void decode16x8(uint4 raw, float (&x)[8]) {
+__device__ __forceinline__ void decode16x8(uint4 raw, f32x8 &x) {
     if (OUT == SCONE_OUT_BF16) decode_bf16x8(raw, x);
     else decode_fp16x8(raw, x);
 }
 template <int OUT>
-__device__ __forceinline__ uint4 pack16x8(const float (&x)[8]) {
+__device__ __forceinline__ uint4 pack16x8(const f32x8 &x) {
     return OUT == SCONE_OUT_BF16 ? pack_bf16x8(x) : pack_fp16x8(x);
 }
 
@@ -90,14 +100,17 @@ __device__ __forceinline__ void stream_hit(const EmbedParams &p, int32_t fid, ui
     float rs = 1.0f;
     if (QUANT == SCONE_QUANT_INT8) rs = __ldg(reinterpret_cast<const float *>(row + p.scale_off));
     for (int c0 = lane; c0 < nchunks; c0 += 32 * U) {
-        uint4 raw[U];
+        uint4 raw[U], rawb[U];  // rawb: second half of an fp32 chunk
         float sc[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int c = c0 + 32 * u;
             sc[u] = rs;
             if (c < nchunks) {
-                if (QUANT == SCONE_QUANT_FP16) {
+                if (QUANT == SCONE_QUANT_FP32) {
+                    raw[u] = ldg_stream_16(row + c * 32, pol);
+                    rawb[u] = ldg_stream_16(row + c * 32 + 16, pol);
+                } else if (QUANT == SCONE_QUANT_FP16) {
                     raw[u] = ldg_stream_16(row + c * 16, pol);
                 } else if (QUANT == SCONE_QUANT_INT8) {
                     const uint2 v = ldg_stream_8(row + c * 8, pol);
@@ -117,8 +130,9 @@ __device__ __forceinline__ void stream_hit(const EmbedParams &p, int32_t fid, ui
                 if (QUANT == SCONE_QUANT_FP16 && OUT == SCONE_OUT_FP16) {
                     o = raw[u];
                 } else {
-                    float x[8];
-                    if (QUANT == SCONE_QUANT_FP16) decode_fp16x8(raw[u], x);
+                    f32x8 x;
+                    if (QUANT == SCONE_QUANT_FP32) decode_fp32x8(raw[u], rawb[u], x);
+                    else if (QUANT == SCONE_QUANT_FP16) decode_fp16x8(raw[u], x);
                     else if (QUANT == SCONE_QUANT_INT8) decode_int8x8(make_uint2(raw[u].x, raw[u].y), sc[u], x);
                     else decode_int4x8(raw[u].x, sc[u], x);
                     o = pack16x8<OUT>(x);
@@ -159,9 +173,11 @@ __device__ __noinline__ void stream_general(const EmbedParams &p, int32_t fid, i
     const uint8_t *arow = (p.additive && fid >= 0 && tok >= 0) ? p.base + (int64_t)tok * p.D * 2 : nullptr;
     const uint8_t *prow = p.pos ? p.pos + pos_in_row(t, p.L, p.T) * p.D * 2 : nullptr;
     for (int c = lane; c < nchunks; c += 32) {
-        float x[8];
+        f32x8 x;
         if (row) {
-            if (QUANT == SCONE_QUANT_FP16) {
+            if (QUANT == SCONE_QUANT_FP32) {
+                decode_fp32x8(ldg_stream_16(row + c * 32), ldg_stream_16(row + c * 32 + 16), x);
+            } else if (QUANT == SCONE_QUANT_FP16) {
                 decode_fp16x8(ldg_stream_16(row + c * 16), x);
             } else if (QUANT == SCONE_QUANT_INT8) {
                 decode_int8x8(ldg_stream_8(row + c * 8), __ldg(reinterpret_cast<const float *>(row + p.scale_off)), x);
@@ -172,20 +188,17 @@ __device__ __noinline__ void stream_general(const EmbedParams &p, int32_t fid, i
         } else if (brow) {
             decode16x8<OUT>(ldg_stream_16(brow + c * 16), x);
         } else {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) x[k] = 0.0f;
+            zero8(x);
         }
         if (arow) {  // wte(ids) + f-gram row
-            float y[8];
+            f32x8 y;
             decode16x8<OUT>(ldg_stream_16(arow + c * 16), y);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) x[k] = __fadd_rn(y[k], x[k]);
+            add8(x, y);
         }
         if (prow) {
-            float y[8];
+            f32x8 y;
             decode16x8<OUT>(__ldg(reinterpret_cast<const uint4 *>(prow + c * 16)), y);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) x[k] = __fadd_rn(x[k], y[k]);
+            add8(x, y);
         }
         stg_stream_16(dst + c * 16, pack16x8<OUT>(x));
     }
@@ -318,6 +331,21 @@ struct BulkLayout {
     int smem_bytes;  // dynamic shared memory per CTA
 };
 
+// 8 elements (chunk c) of a table row staged in shared memory -> fp32
+template <int QUANT>
+__device__ __forceinline__ void decode_smem(const EmbedParams &p, const uint8_t *srow, int c, float rs, f32x8 &x) {
+    if (QUANT == SCONE_QUANT_FP32) {
+        decode_fp32x8(*reinterpret_cast<const uint4 *>(srow + c * 32), *reinterpret_cast<const uint4 *>(srow + c * 32 + 16), x);
+    } else if (QUANT == SCONE_QUANT_FP16) {
+        decode_fp16x8(*reinterpret_cast<const uint4 *>(srow + c * 16), x);
+    } else if (QUANT == SCONE_QUANT_INT8) {
+        decode_int8x8(*reinterpret_cast<const uint2 *>(srow + c * 8), rs, x);
+    } else {
+        const float sc = __half2float(*(reinterpret_cast<const __half *>(srow + p.scale_off) + (c >> p.group_shift)));
+        decode_int4x8(*reinterpret_cast<const uint32_t *>(srow + c * 4), sc, x);
+    }
+}
+
 template <int QUANT, int OUT>
 __device__ __forceinline__ void stream_from_smem(const EmbedParams &p, const uint8_t *srow, const uint8_t *arow, const uint8_t *prow,
                                                  int32_t fid, int32_t tok, uint8_t *__restrict__ dst, int lane, uint64_t pol) {
@@ -331,15 +359,8 @@ __device__ __forceinline__ void stream_from_smem(const EmbedParams &p, const uin
             if (QUANT == SCONE_QUANT_FP16 && OUT == SCONE_OUT_FP16) {
                 o = *reinterpret_cast<const uint4 *>(srow + c * 16);
             } else {
-                float x[8];
-                if (QUANT == SCONE_QUANT_FP16) {
-                    decode_fp16x8(*reinterpret_cast<const uint4 *>(srow + c * 16), x);
-                } else if (QUANT == SCONE_QUANT_INT8) {
-                    decode_int8x8(*reinterpret_cast<const uint2 *>(srow + c * 8), rs, x);
-                } else {
-                    const float sc = __half2float(*(reinterpret_cast<const __half *>(srow + p.scale_off) + (c >> p.group_shift)));
-                    decode_int4x8(*reinterpret_cast<const uint32_t *>(srow + c * 4), sc, x);
-                }
+                f32x8 x;
+                decode_smem<QUANT>(p, srow, c, rs, x);
                 o = pack16x8<OUT>(x);
             }
             stg_stream_16(dst + c * 16, o, pol);
@@ -356,33 +377,23 @@ __device__ __forceinline__ void stream_from_smem(const EmbedParams &p, const uin
             for (int u = 0; u < 4; ++u) {
                 const int c = c0 + 32 * u;
                 if (c >= nchunks) continue;
-                float x[8];
+                f32x8 x;
                 if (fid >= 0) {
-                    if (QUANT == SCONE_QUANT_FP16) {
-                        decode_fp16x8(*reinterpret_cast<const uint4 *>(srow + c * 16), x);
-                    } else if (QUANT == SCONE_QUANT_INT8) {
-                        decode_int8x8(*reinterpret_cast<const uint2 *>(srow + c * 8), rs, x);
-                    } else {
-                        const float sc = __half2float(*(reinterpret_cast<const __half *>(srow + p.scale_off) + (c >> p.group_shift)));
-                        decode_int4x8(*reinterpret_cast<const uint32_t *>(srow + c * 4), sc, x);
-                    }
+                    decode_smem<QUANT>(p, srow, c, rs, x);
                 } else if (tok >= 0) {
                     decode16x8<OUT>(*reinterpret_cast<const uint4 *>(srow + c * 16), x);
                 } else {
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) x[k] = 0.0f;
+                    zero8(x);
                 }
                 if (arow) {  // wte(ids) + f-gram row
-                    float y[8];
+                    f32x8 y;
                     decode16x8<OUT>(*reinterpret_cast<const uint4 *>(arow + c * 16), y);
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) x[k] = __fadd_rn(y[k], x[k]);
+                    add8(x, y);
                 }
                 if (prow) {
-                    float y[8];
+                    f32x8 y;
                     decode16x8<OUT>(*reinterpret_cast<const uint4 *>(prow + c * 16), y);
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) x[k] = __fadd_rn(x[k], y[k]);
+                    add8(x, y);
                 }
                 stg_stream_16(dst + c * 16, pack16x8<OUT>(x), pol);
             }
@@ -433,8 +444,15 @@ __global__ void __launch_bounds__(32 * (NM + NG), MINB) embed_bulk_kernel(const 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    // everything above overlapped the previous kernel's tail; nothing below may run before it has completed
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // Everything above overlapped the previous kernel's tail.  By default nothing below may run before that kernel has
+    // completed.  With SCONE_EMBED_INPUTS_STABLE the caller vouches that no INPUT of this call (ids, index, table rows,
+    // base / position rows) is written by the kernel that precedes it in the stream: matching and the row copies into
+    // shared memory then start at once -- the whole dependent chain ids -> slot -> row runs under the previous kernel's
+    // tail -- and only the first WRITE to global memory (fgram_id / match_len here, the embeddings in the gather warps)
+    // waits for the previous grid.
+    const bool early = (p.flags & SCONE_EMBED_INPUTS_STABLE) != 0;
+    bool waited = !early;
+    if (!early) griddep_wait();
     SCONE_STAMP(0, threadIdx.x == 0);
 
     if (warp < NM) {
@@ -457,7 +475,7 @@ __global__ void __launch_bounds__(32 * (NM + NG), MINB) embed_bulk_kernel(const 
             const int64_t i = base + j;
             const int64_t ntile = tile + (int64_t)NM * gridDim.x;
             int32_t ntok = -1;
-            int32_t fid = -1, tok = -1;
+            int32_t fid = -1, tok = -1, mlen = 0;
             if (p.fgram_in) {
                 if (i < p.T) {
                     fid = __ldg(p.fgram_in + i);
@@ -473,12 +491,9 @@ __global__ void __launch_bounds__(32 * (NM + NG), MINB) embed_bulk_kernel(const 
                 const WindowMatch m = match_window<P>(p.ix, wtok, p.T, p.L, base, lane, back);
                 SCONE_STAMP(2, warp == 0 && lane == 0 && it == 0 && m.fid != -12345);  // first tile resolved
                 fid = m.fid;
+                mlen = m.len;
                 tok = own_token<P>(wtok, lane, back);
                 if ((int64_t)tok >= p.V) tok = -1;
-                if ((lane % P) == 0 && i < p.T) {
-                    if (p.out_id) p.out_id[i] = m.fid;
-                    if (p.out_len) p.out_len[i] = (uint8_t)m.len;
-                }
                 wtok = ntok;
             }
             if (fid != -1 && !(ADD && fid >= 0)) tok = -1;  // additive: a hit still needs its base row
@@ -519,6 +534,15 @@ __global__ void __launch_bounds__(32 * (NM + NG), MINB) embed_bulk_kernel(const 
             if (src2) bulk_g2s(slot + lay.pos_off, src2, (uint32_t)p.D * 2u, &full_bar[q], policy_evict_last());
             if (src3) bulk_g2s(slot + add_off, src3, (uint32_t)p.D * 2u, &full_bar[q], pol);
             SCONE_STAMP(3, warp == 0 && lane == 0 && it == 0);                        // first bulk copies issued
+            // the match result is this warp's only global write: after the previous grid (see `early` above)
+            if (!waited) {
+                griddep_wait();
+                waited = true;
+            }
+            if (!p.fgram_in && owner) {
+                if (p.out_id) p.out_id[i] = fid;
+                if (p.out_len) p.out_len[i] = (uint8_t)mlen;
+            }
         }
         SCONE_STAMP(7, warp == 0 && lane == 0);                                       // matcher 0 done
     } else {
@@ -531,6 +555,10 @@ __global__ void __launch_bounds__(32 * (NM + NG), MINB) embed_bulk_kernel(const 
             const int q = (int)(itl % R);
             mbar_wait(&full_bar[q], (uint32_t)((itl / R) & 1));
             SCONE_STAMP(4, w == 0 && lane == 0 && itl == 0);                          // first rows have landed
+            if (!waited) {  // rows are staged; the stores below are the first thing that must follow the previous grid
+                griddep_wait();
+                waited = true;
+            }
             const int first = (int)(((int64_t)w - (itl * G) % NG + NG) % NG);
             for (int j = first; j < G; j += NG) {
                 const int2 e = ring[q * G + j];

@@ -308,7 +308,7 @@ int scone_index_lookup(const scone_index_t *index, const int64_t *d_ids, int64_t
     IndexView v = view_of(ix, T);
     const int P = lanes_per_position(ix->len_mask, ix->max_n);
     const int64_t windows = (T + (32 / P) - 1) / (32 / P);
-    const unsigned blocks = (unsigned)((windows + 7) / 8);
+    SCONE_GRID(blocks, (windows + 7) / 8, "scone_index_lookup");
     switch (P) {
         case 1: lookup_kernel<1><<<blocks, 256, 0, stream>>>(v, d_ids, T, L, d_out_id, d_out_len); break;
         case 2: lookup_kernel<2><<<blocks, 256, 0, stream>>>(v, d_ids, T, L, d_out_id, d_out_len); break;
@@ -331,7 +331,7 @@ int scone_index_match_all(const scone_index_t *index, const int64_t *d_ids, int6
     IndexView v = view_of(ix, T);
     const int P = lanes_dense(ix->max_n);
     const int64_t windows = (T + (32 / P) - 1) / (32 / P);
-    const unsigned blocks = (unsigned)((windows + 7) / 8);
+    SCONE_GRID(blocks, (windows + 7) / 8, "scone_index_match_all");
     switch (P) {
         case 1: match_all_kernel<1><<<blocks, 256, 0, stream>>>(v, d_ids, T, L, d_out); break;
         case 2: match_all_kernel<2><<<blocks, 256, 0, stream>>>(v, d_ids, T, L, d_out); break;

@@ -114,8 +114,15 @@ int scone_pipeline_submit(scone_pipeline_t *pp, const int64_t *h_ids_pinned, int
     SCONE_CUDA(cudaStreamWaitEvent(p->s_run, p->ev_in[s], 0));
     SCONE_CUDA(cudaStreamWaitEvent(p->s_run, p->ev_out[s], 0));
     uint8_t *meta = static_cast<uint8_t *>(p->d_meta[s]);
-    int rc = scone_embed_forward(p->index, &p->table, p->base, p->base_rows, p->pos, static_cast<const int64_t *>(p->d_ids[s]), p->B, p->L,
-                                 p->d_out[s], p->out_dtype, reinterpret_cast<int32_t *>(meta), meta + 4 * T, p->status, p->s_run);
+    // The kernel that precedes this one on s_run is the pipeline's own previous batch, which writes only another slot's
+    // outputs; this batch's ids arrive by the copy above (an event dependency, not a kernel) and the tables are static
+    // while the pipeline runs (scone_pipeline_follow orders it behind a caller's update): SCONE_EMBED_INPUTS_STABLE holds,
+    // so consecutive batches overlap -- batch k+1 matches and fetches rows under batch k's tail.
+    scone_embed_opts_t opts{};
+    opts.flags = SCONE_EMBED_INPUTS_STABLE;
+    int rc = scone_embed_forward_ex(p->index, &p->table, p->base, p->base_rows, p->pos, static_cast<const int64_t *>(p->d_ids[s]), p->B,
+                                    p->L, p->d_out[s], p->out_dtype, reinterpret_cast<int32_t *>(meta), meta + 4 * T, p->status, &opts,
+                                    p->s_run);
     if (rc != SCONE_OK) return rc;
     SCONE_CUDA(cudaEventRecord(p->ev_run[s], p->s_run));
     // copy-out
@@ -125,6 +132,23 @@ int scone_pipeline_submit(scone_pipeline_t *pp, const int64_t *h_ids_pinned, int
     p->busy[s] = 1;
     p->k += 1;
     if (slot_out) *slot_out = s;
+    return SCONE_OK;
+}
+
+int scone_pipeline_follow(scone_pipeline_t *pp, void *stream) {
+    SCONE_REQUIRE(pp, "scone_pipeline_follow: NULL pipeline");
+    Pipeline *p = reinterpret_cast<Pipeline *>(pp);
+    cudaEvent_t ev;
+    SCONE_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    cudaError_t e = cudaEventRecord(ev, (cudaStream_t)stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(p->s_in, ev, 0);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(p->s_run, ev, 0);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(p->s_out, ev, 0);
+    cudaEventDestroy(ev);  // released once the recorded work has completed
+    if (e != cudaSuccess) {
+        set_error("scone_pipeline_follow failed: %s", cudaGetErrorString(e));
+        return SCONE_E_CUDA;
+    }
     return SCONE_OK;
 }
 

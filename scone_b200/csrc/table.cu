@@ -10,14 +10,16 @@ namespace scone {
 
 int check_table(const scone_table_desc_t *t, const char *who) {
     SCONE_REQUIRE(t->d_rows != nullptr || t->num_rows == 0, "%s: table rows pointer is NULL", who);
-    SCONE_REQUIRE(t->quant >= SCONE_QUANT_FP16 && t->quant <= SCONE_QUANT_INT4, "%s: unknown quant %d", who, t->quant);
+    SCONE_REQUIRE(t->quant >= SCONE_QUANT_FP16 && t->quant <= SCONE_QUANT_FP32, "%s: unknown quant %d", who, t->quant);
     SCONE_REQUIRE(t->dim > 0 && t->dim % 8 == 0, "%s: dim %d must be a positive multiple of 8", who, t->dim);
     SCONE_REQUIRE(t->dim <= (1 << 20), "%s: dim %d too large", who, t->dim);
     SCONE_REQUIRE(t->row_stride > 0 && t->row_stride % 16 == 0, "%s: row_stride %lld must be a positive multiple of 16", who,
                   (long long)t->row_stride);
     SCONE_REQUIRE(((uintptr_t)t->d_rows & 15) == 0, "%s: table rows pointer must be 16-byte aligned", who);
     int64_t need = 0;
-    if (t->quant == SCONE_QUANT_FP16) {
+    if (t->quant == SCONE_QUANT_FP32) {
+        need = 4ll * t->dim;
+    } else if (t->quant == SCONE_QUANT_FP16) {
         need = 2ll * t->dim;
     } else if (t->quant == SCONE_QUANT_INT8) {
         SCONE_REQUIRE(t->scale_offset >= t->dim && t->scale_offset % 4 == 0, "%s: INT8 scale_offset %d invalid", who, t->scale_offset);
@@ -56,7 +58,9 @@ __global__ void __launch_bounds__(256) store_kernel(uint8_t *rows, int64_t row_s
     }
     const float *x = src + r * D;
     uint8_t *o = rows + dst_row * row_stride;
-    if (QUANT == SCONE_QUANT_FP16) {
+    if (QUANT == SCONE_QUANT_FP32) {  // unquantised: the reference's own storage (embedding_cache.py:99, :111)
+        for (int d = lane * 4; d < D; d += 128) *reinterpret_cast<float4 *>(o + d * 4) = *reinterpret_cast<const float4 *>(x + d);
+    } else if (QUANT == SCONE_QUANT_FP16) {
         for (int d = lane * 2; d < D; d += 64) {
             const float2 v = *reinterpret_cast<const float2 *>(x + d);
             *reinterpret_cast<__half2 *>(o + d * 2) = __floats2half2_rn(v.x, v.y);
@@ -103,6 +107,21 @@ __global__ void __launch_bounds__(256) store_kernel(uint8_t *rows, int64_t row_s
     }
 }
 
+// 8 elements (chunk c) of a stored row in global memory -> fp32
+template <int QUANT>
+__device__ __forceinline__ void decode_row_chunk(const uint8_t *row, int c, int scale_off, int group_shift, f32x8 &x) {
+    if (QUANT == SCONE_QUANT_FP32) {
+        decode_fp32x8(ldg_stream_16(row + c * 32), ldg_stream_16(row + c * 32 + 16), x);
+    } else if (QUANT == SCONE_QUANT_FP16) {
+        decode_fp16x8(ldg_stream_16(row + c * 16), x);
+    } else if (QUANT == SCONE_QUANT_INT8) {
+        decode_int8x8(ldg_stream_8(row + c * 8), __ldg(reinterpret_cast<const float *>(row + scale_off)), x);
+    } else {
+        const __half hs = __ldg(reinterpret_cast<const __half *>(row + scale_off) + (c >> group_shift));
+        decode_int4x8(ldg_stream_4(row + c * 4), __half2float(hs), x);
+    }
+}
+
 // One warp per requested row: out[r] = dequant(table[ids[r]]) as fp32 / bf16 / fp16.
 template <int QUANT, int OUT>
 __global__ void __launch_bounds__(256) gather_kernel(const uint8_t *__restrict__ rows, int64_t row_stride, int64_t num_rows, int D,
@@ -118,22 +137,13 @@ __global__ void __launch_bounds__(256) gather_kernel(const uint8_t *__restrict__
     const int nchunks = D >> 3;
     constexpr int OB = OUT == SCONE_OUT_FP32 ? 4 : 2;
     for (int c = lane; c < nchunks; c += 32) {
-        float x[8];
-        if (!ok) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) x[e] = 0.0f;
-        } else if (QUANT == SCONE_QUANT_FP16) {
-            decode_fp16x8(ldg_stream_16(row + c * 16), x);
-        } else if (QUANT == SCONE_QUANT_INT8) {
-            decode_int8x8(ldg_stream_8(row + c * 8), __ldg(reinterpret_cast<const float *>(row + scale_off)), x);
-        } else {
-            const __half hs = __ldg(reinterpret_cast<const __half *>(row + scale_off) + (c >> group_shift));
-            decode_int4x8(ldg_stream_4(row + c * 4), __half2float(hs), x);
-        }
+        f32x8 x;
+        if (!ok) zero8(x);
+        else decode_row_chunk<QUANT>(row, c, scale_off, group_shift, x);
         uint8_t *o = out + ((int64_t)r * D + c * 8) * OB;
         if (OUT == SCONE_OUT_FP32) {
-            *reinterpret_cast<float4 *>(o) = make_float4(x[0], x[1], x[2], x[3]);
-            *reinterpret_cast<float4 *>(o + 16) = make_float4(x[4], x[5], x[6], x[7]);
+            *reinterpret_cast<float4 *>(o) = make_float4(x[0].x, x[0].y, x[1].x, x[1].y);
+            *reinterpret_cast<float4 *>(o + 16) = make_float4(x[2].x, x[2].y, x[3].x, x[3].y);
         } else if (OUT == SCONE_OUT_BF16) {
             *reinterpret_cast<uint4 *>(o) = pack_bf16x8(x);
         } else {
@@ -196,31 +206,21 @@ __global__ void __launch_bounds__(256) mean_kernel(const uint8_t *__restrict__ r
     const int nchunks = D >> 3;
     constexpr int OB = OUT == SCONE_OUT_FP32 ? 4 : 2;
     for (int c = lane; c < nchunks; c += 32) {
-        float acc[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] = 0.0f;
+        f32x8 acc;
+        zero8(acc);
         for (int r = 0; r < k; ++r) {
-            const uint8_t *row = rows + (int64_t)ids[r] * row_stride;
-            float x[8];
-            if (QUANT == SCONE_QUANT_FP16) {
-                decode_fp16x8(ldg_stream_16(row + c * 16), x);
-            } else if (QUANT == SCONE_QUANT_INT8) {
-                decode_int8x8(ldg_stream_8(row + c * 8), __ldg(reinterpret_cast<const float *>(row + scale_off)), x);
-            } else {
-                const __half hs = __ldg(reinterpret_cast<const __half *>(row + scale_off) + (c >> group_shift));
-                decode_int4x8(ldg_stream_4(row + c * 4), __half2float(hs), x);
-            }
-#pragma unroll
-            for (int e = 0; e < 8; ++e) acc[e] = __fadd_rn(acc[e], x[e]);
+            f32x8 x;
+            decode_row_chunk<QUANT>(rows + (int64_t)ids[r] * row_stride, c, scale_off, group_shift, x);
+            add8(acc, x);
         }
         if (k > 1) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) acc[e] = __fdiv_rn(acc[e], (float)k);
+            for (int e = 0; e < 4; ++e) acc[e] = make_float2(__fdiv_rn(acc[e].x, (float)k), __fdiv_rn(acc[e].y, (float)k));
         }
         uint8_t *o = out + (t * D + c * 8) * OB;
         if (OUT == SCONE_OUT_FP32) {
-            *reinterpret_cast<float4 *>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-            *reinterpret_cast<float4 *>(o + 16) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+            *reinterpret_cast<float4 *>(o) = make_float4(acc[0].x, acc[0].y, acc[1].x, acc[1].y);
+            *reinterpret_cast<float4 *>(o + 16) = make_float4(acc[2].x, acc[2].y, acc[3].x, acc[3].y);
         } else if (OUT == SCONE_OUT_BF16) {
             *reinterpret_cast<uint4 *>(o) = pack_bf16x8(acc);
         } else {
@@ -268,7 +268,9 @@ int scone_table_layout(int32_t quant, int32_t dim, int32_t group, int32_t align,
     SCONE_REQUIRE(align % 16 == 0, "scone_table_layout: align %d must be a multiple of 16", align);
     int64_t bytes;
     int32_t soff = 0;
-    if (quant == SCONE_QUANT_FP16) {
+    if (quant == SCONE_QUANT_FP32) {
+        bytes = 4ll * dim;
+    } else if (quant == SCONE_QUANT_FP16) {
         bytes = 2ll * dim;
     } else if (quant == SCONE_QUANT_INT8) {
         soff = dim;
@@ -300,8 +302,10 @@ int scone_table_store(const scone_table_desc_t *table, const float *d_rows_f32, 
     SCONE_REQUIRE(d_row_ids || (row_base >= 0 && row_base + k <= table->num_rows), "scone_table_store: rows [%lld, %lld) outside the table",
                   (long long)row_base, (long long)(row_base + k));
     uint8_t *rows = static_cast<uint8_t *>(const_cast<void *>(table->d_rows));
-    const unsigned blocks = (unsigned)((k + 7) / 8);
-    if (table->quant == SCONE_QUANT_FP16)
+    SCONE_GRID(blocks, (k + 7) / 8, "scone_table_store");
+    if (table->quant == SCONE_QUANT_FP32)
+        store_kernel<SCONE_QUANT_FP32><<<blocks, 256, 0, stream>>>(rows, table->row_stride, table->num_rows, table->dim, 0, 0, d_rows_f32, d_row_ids, row_base, k, nullptr);
+    else if (table->quant == SCONE_QUANT_FP16)
         store_kernel<SCONE_QUANT_FP16><<<blocks, 256, 0, stream>>>(rows, table->row_stride, table->num_rows, table->dim, 0, 0, d_rows_f32, d_row_ids, row_base, k, nullptr);
     else if (table->quant == SCONE_QUANT_INT8)
         store_kernel<SCONE_QUANT_INT8><<<blocks, 256, 0, stream>>>(rows, table->row_stride, table->num_rows, table->dim, 0, table->scale_offset, d_rows_f32, d_row_ids, row_base, k, nullptr);
@@ -329,8 +333,9 @@ int scone_embed_mean_forward(const scone_index_t *index, const scone_table_desc_
     int group_shift = 0;
     if (table->quant == SCONE_QUANT_INT4)
         while ((1 << group_shift) < table->group / 8) ++group_shift;
-    const unsigned blocks = (unsigned)((T + 7) / 8);
-    if (table->quant == SCONE_QUANT_FP16) launch_mean<SCONE_QUANT_FP16>(out_dtype, blocks, stream, table, group_shift, d_work, ix->max_n, T, L, d_out);
+    SCONE_GRID(blocks, (T + 7) / 8, "scone_embed_mean_forward");
+    if (table->quant == SCONE_QUANT_FP32) launch_mean<SCONE_QUANT_FP32>(out_dtype, blocks, stream, table, group_shift, d_work, ix->max_n, T, L, d_out);
+    else if (table->quant == SCONE_QUANT_FP16) launch_mean<SCONE_QUANT_FP16>(out_dtype, blocks, stream, table, group_shift, d_work, ix->max_n, T, L, d_out);
     else if (table->quant == SCONE_QUANT_INT8) launch_mean<SCONE_QUANT_INT8>(out_dtype, blocks, stream, table, group_shift, d_work, ix->max_n, T, L, d_out);
     else launch_mean<SCONE_QUANT_INT4>(out_dtype, blocks, stream, table, group_shift, d_work, ix->max_n, T, L, d_out);
     SCONE_LAUNCHED();
@@ -347,7 +352,7 @@ int scone_table_gather_packed(const scone_table_desc_t *table, const int32_t *d_
     if (k == 0) return SCONE_OK;
     SCONE_REQUIRE(d_row_ids && d_out, "scone_table_gather_packed: NULL buffer");
     SCONE_REQUIRE(((uintptr_t)d_out & 15) == 0, "scone_table_gather_packed: out must be 16-byte aligned");
-    const unsigned blocks = (unsigned)((k + 7) / 8);
+    SCONE_GRID(blocks, (k + 7) / 8, "scone_table_gather_packed");
     gather_packed_kernel<<<blocks, 256, 0, stream>>>(static_cast<const uint8_t *>(table->d_rows), table->row_stride, table->num_rows,
                                                     d_row_ids, k, static_cast<uint8_t *>(d_out), d_status);
     SCONE_LAUNCHED();
@@ -367,8 +372,9 @@ int scone_table_gather(const scone_table_desc_t *table, const int64_t *d_row_ids
     int group_shift = 0;
     if (table->quant == SCONE_QUANT_INT4)
         while ((1 << group_shift) < table->group / 8) ++group_shift;
-    const unsigned blocks = (unsigned)((k + 7) / 8);
-    if (table->quant == SCONE_QUANT_FP16) launch_gather<SCONE_QUANT_FP16>(out_dtype, blocks, stream, table, group_shift, d_row_ids, k, d_out, d_status);
+    SCONE_GRID(blocks, (k + 7) / 8, "scone_table_gather");
+    if (table->quant == SCONE_QUANT_FP32) launch_gather<SCONE_QUANT_FP32>(out_dtype, blocks, stream, table, group_shift, d_row_ids, k, d_out, d_status);
+    else if (table->quant == SCONE_QUANT_FP16) launch_gather<SCONE_QUANT_FP16>(out_dtype, blocks, stream, table, group_shift, d_row_ids, k, d_out, d_status);
     else if (table->quant == SCONE_QUANT_INT8) launch_gather<SCONE_QUANT_INT8>(out_dtype, blocks, stream, table, group_shift, d_row_ids, k, d_out, d_status);
     else launch_gather<SCONE_QUANT_INT4>(out_dtype, blocks, stream, table, group_shift, d_row_ids, k, d_out, d_status);
     SCONE_LAUNCHED();

@@ -1,9 +1,10 @@
 """Drop-in ``EmbeddingCache`` (mirror of reference ``scone/inference/embedding_cache.py``).
 
 Same constructor / methods as the reference class.  Rows live in a packed device table
-(FP16 / INT8 / INT4, ``scone_b200.table.CacheTable``) instead of a dict of fp32 numpy rows or an
-fp32 ``np.memmap``; ``use_memory_map=True`` (the reference's "table does not live in RAM" switch,
-:69-103) selects the offloaded tier: pinned host memory read zero-copy by the GPU.
+(``scone_b200.table.CacheTable``) instead of a dict of fp32 numpy rows or an fp32 ``np.memmap``:
+unquantised fp32 by default -- what the reference stores and returns, bit for bit (:84-91, :132-135) --
+or FP16 / INT8 / INT4 with ``quant=``; ``use_memory_map=True`` (the reference's "table does not live in
+RAM" switch, :69-103) selects the offloaded tier: pinned host memory read zero-copy by the GPU.
 
 Added for the fused path: :meth:`set_base_embedding` and :meth:`lookup`, which run
 match + gather + dequant + fallback for a whole ``[B, L]`` batch in one kernel.
@@ -50,7 +51,7 @@ class _RowsView(Mapping):
     def __getitem__(self, key) -> np.ndarray:
         if key not in self:
             raise KeyError(key)
-        return self._c._table.gather(torch.tensor([int(key)], device=self._c.device)).cpu().numpy()[0]
+        return self._c._gather_rows(torch.tensor([int(key)], device=self._c.device)).cpu().numpy()[0]
 
 
 class EmbeddingCache:
@@ -64,13 +65,14 @@ class EmbeddingCache:
         cache_dir: Optional[str] = None,
         use_memory_map: bool = False,
         *,
-        quant: str = "fp16",
+        quant: str = "fp32",
         group_size: int = 128,
         out_dtype: torch.dtype = torch.bfloat16,
         device: Optional[torch.device] = None,
         tier: Optional[str] = None,
     ) -> None:
-        """``quant``: "fp16" | "int8" | "int4" (``group_size`` for int4); ``tier``: "hbm" (default), "host" (pinned host
+        """``quant``: "fp32" (default: rows kept exactly as given, like the reference) | "fp16" | "int8" | "int4"
+        (``group_size`` for int4); ``tier``: "hbm" (default), "host" (pinned host
         memory, also selected by ``use_memory_map=True``) or "sharded" (rows split by id % world over the default
         process group and read over NVLink; needs ``torch.distributed`` initialised with NCCL)."""
         self.n_gram_extractor = n_gram_extractor
@@ -88,6 +90,9 @@ class EmbeddingCache:
         self._pos_emb: Optional[torch.Tensor] = None
         self._status: Optional[torch.Tensor] = None
         self._sharded = None
+        self._missing: Optional[int] = None     # cached: number of vocabulary rows never stored (None = not counted yet)
+        if quant not in ("fp32", "fp16", "int8", "int4"):
+            raise ValueError("quant must be 'fp32', 'fp16', 'int8' or 'int4'")
         if self.tier not in ("hbm", "host", "sharded"):
             raise ValueError("tier must be 'hbm', 'host' or 'sharded'")
         if self.cache_dir is not None and not os.path.exists(self.cache_dir):
@@ -131,6 +136,8 @@ class EmbeddingCache:
             return None
         st = self._table.storage.numpy()
         D = self.embedding_dim
+        if self.quant == "fp32":
+            return st[:, :4 * D].view(np.float32)      # the reference's own memmap: [N, D] float32 (:84-91)
         if self.quant == "fp16":
             return st[:, :2 * D].view(np.float16)
         if self.quant == "int8":
@@ -150,6 +157,8 @@ class EmbeddingCache:
             ids = [int(k) for k, _ in items]
             embeddings = torch.stack([torch.as_tensor(v, dtype=torch.float32).cpu() for _, v in items]) if items \
                 else torch.zeros((0, self.embedding_dim))
+        elif isinstance(f_gram_ids, (torch.Tensor, np.ndarray, range)):
+            ids = f_gram_ids                       # bulk form: no per-id Python objects (10^7-row tables)
         else:
             ids = [int(i) for i in f_gram_ids]
         if embeddings is None:
@@ -158,9 +167,13 @@ class EmbeddingCache:
         if embeddings.dim() != 2 or embeddings.shape[1] != self.embedding_dim or embeddings.shape[0] != len(ids):
             raise ValueError(f"embeddings must be [{len(ids)}, {self.embedding_dim}]")
         table = self.table
-        id_t = torch.tensor(ids, dtype=torch.int64, device=self.device)
+        if isinstance(ids, range):
+            id_t = torch.arange(ids.start, ids.stop, ids.step, dtype=torch.int64, device=self.device)
+        else:
+            id_t = torch.as_tensor(ids, dtype=torch.int64).to(self.device)
         if len(ids) and (int(id_t.min()) < 0 or int(id_t.max()) >= len(self.n_gram_extractor)):
             raise IndexError("f-gram id out of range")                                     # memmap backend: IndexError
+        self._missing = None
         if self.tier == "sharded":
             # every rank may be handed every row; each keeps the ones it owns.  Call publish() after the last store.
             self._sharded.store_owned(embeddings.to(torch.float32), id_t)
@@ -190,10 +203,25 @@ class EmbeddingCache:
                 raise (IndexError if self.use_memory_map else KeyError)(int(ids[bad][0]))
             if not self.use_memory_map and not bool(self._present[ids].all()):
                 raise KeyError(int(ids[~self._present[ids]][0]))                           # dict backend: KeyError (:139)
-        out = self._table.gather(ids, torch.float32)
+        out = self._gather_rows(ids)
         if device is None:
             return out.cpu()
         return out.to(device)
+
+    def _gather_rows(self, ids: torch.Tensor) -> torch.Tensor:
+        """dequant(table[ids]) as fp32 [k, D] for GLOBAL f-gram ids.  On the sharded tier row ``id`` lives on rank
+        ``id % W`` at local row ``id // W``: each owner's rows are read through its peer-mapped shard (NVLink), so the
+        reference-API methods see the whole table from every rank (the peers must have called :meth:`publish`)."""
+        if self.tier != "sharded":
+            return self._table.gather(ids, torch.float32)
+        sh = self._sharded
+        out = torch.empty((ids.numel(), self.embedding_dim), dtype=torch.float32, device=self.device)
+        owner = ids % sh.world
+        for r in range(sh.world):
+            sel = torch.nonzero(owner == r).flatten()
+            if sel.numel():
+                out[sel] = sh.shard_view(r).gather(torch.div(ids[sel], sh.world, rounding_mode="floor"), torch.float32)
+        return out
 
     def get_token_embeddings(self, token_ids: List[int], device: Optional[torch.device] = None) -> Dict[int, torch.Tensor]:
         """pos -> [k_pos, D] rows of all f-grams containing the position (reference :149-181); one match_all
@@ -232,19 +260,35 @@ class EmbeddingCache:
         self._pos_emb = None if position_weight is None else \
             position_weight.detach().to(device=self.device, dtype=self.out_dtype).contiguous()
 
+    def _require_all_rows(self) -> None:
+        """The reference raises KeyError when a matched f-gram has no cached row (``embedding_cache.py:139``).  The fused
+        kernels do not consult the presence mask per position, so the check is made once per change of the table: every
+        vocabulary row must have been stored before the first ``lookup``."""
+        if self._missing is None:
+            self.table
+            self._missing = int((~self._present).sum().item())
+        if self._missing:
+            raise KeyError(int(torch.nonzero(~self._present).flatten()[0].item()))
+
     def lookup(self, input_ids: torch.Tensor, out: Optional[torch.Tensor] = None, add_positions: bool = False,
-               combine: str = "replace"):
+               combine: str = "replace", inputs_stable: bool = False, strict: bool = True,
+               out_id: Optional[torch.Tensor] = None, out_len: Optional[torch.Tensor] = None):
         """``input_ids`` long [B, L] on the GPU -> (embeds [B, L, D] out_dtype, fgram_id int32 [B, L], match_len uint8 [B, L]).
 
         embeds[b, i] = dequant(row of the longest f-gram ending at i) or base_emb[input_ids[b, i]].
         ``combine="add"``: the reference code's ``wte(input_ids) + f_gram_embeddings`` (``language_model.py:239-243``)
         instead -- the row is added to the token embedding (hbm / host tiers).  Asynchronous on the current stream.
+        ``strict`` (default): raise ``KeyError`` like the reference if some vocabulary f-gram has no cached row yet
+        (checked once after each ``cache_embeddings``; ``strict=False`` serves such f-grams from zero-filled storage).
+        ``inputs_stable``: see :func:`scone_b200.table.embed_forward`.
         """
         if self._base_emb is None:
             raise RuntimeError("call set_base_embedding(wte.weight) first: misses fall back to the token embedding")
         if add_positions and self._pos_emb is None:
             raise RuntimeError("add_positions=True needs set_base_embedding(..., position_weight=wpe.weight)")
         index = self.n_gram_extractor.device_index(self.device)
+        if strict:
+            self._require_all_rows()
         if self._status is None:
             self._status = torch.zeros((1,), dtype=torch.int32, device=self.device)
         if self.tier == "sharded":
@@ -253,11 +297,11 @@ class EmbeddingCache:
             from ..sharded import embed_forward_sharded
             self.table
             return embed_forward_sharded(index, self._sharded, self._base_emb, input_ids,
-                                         self._pos_emb if add_positions else None, out, self._status)
+                                         self._pos_emb if add_positions else None, out, self._status, out_id, out_len)
         return embed_forward(index, self.table, self._base_emb, input_ids, self._pos_emb if add_positions else None, out,
-                             self._status, combine=combine)
+                             self._status, out_id=out_id, out_len=out_len, combine=combine, inputs_stable=inputs_stable)
 
-    def host_pipeline(self, batch_shape, add_positions: bool = False, slots: int = 4):
+    def host_pipeline(self, batch_shape, add_positions: bool = False, slots: int = 4, strict: bool = True):
         """A :class:`scone_b200.HostPipeline` over this cache for callers whose ids arrive in pinned HOST memory
         (the reference tokenises on the host, ``engine.py:222-233``): copies in and out overlap the kernel."""
         from ..pipeline import HostPipeline
@@ -265,6 +309,8 @@ class EmbeddingCache:
             raise RuntimeError("call set_base_embedding(wte.weight) first")
         if self.tier == "sharded":
             raise ValueError("host_pipeline is for the hbm / host tiers")
+        if strict:
+            self._require_all_rows()
         index = self.n_gram_extractor.device_index(self.device)
         return HostPipeline(index, self.table, self._base_emb, tuple(batch_shape),
                             pos_emb=self._pos_emb if add_positions else None, slots=slots)
@@ -274,6 +320,13 @@ class EmbeddingCache:
         if self.tier == "sharded":
             self.table
             self._sharded.publish()
+
+    def _not_on_sharded(self, what: str) -> None:
+        # a rank holds only ceil(N / W) rows (local row = id // W): persisting or averaging "the table" from one rank
+        # would silently use the wrong rows
+        if self.tier == "sharded":
+            raise NotImplementedError(f"EmbeddingCache.{what} is not available on the row-sharded tier: every rank holds "
+                                      "only its own rows (save each shard from an hbm-tier cache before sharding)")
 
     def status(self) -> int:
         """Sticky device status bits (synchronises): bit 0 = some missed token id was outside the base table."""
@@ -287,7 +340,8 @@ class EmbeddingCache:
         Unlike the reference's raw ``np.memmap`` (``embedding_cache.py:84-89``) it can be reloaded (and memory-mapped)."""
         import struct
         t = self.table
-        hdr = struct.pack("<8sIIIIQIQ", self._MAGIC, 1, {"fp16": 0, "int8": 1, "int4": 2}[self.quant], self.embedding_dim,
+        self._not_on_sharded("save_binary")
+        hdr = struct.pack("<8sIIIIQIQ", self._MAGIC, 1, {"fp16": 0, "int8": 1, "int4": 2, "fp32": 3}[self.quant], self.embedding_dim,
                           self.group_size, t.row_stride, t.scale_offset, t.num_rows)
         with open(path, "wb") as f:
             f.write(hdr.ljust(64, b"\x00"))
@@ -307,7 +361,7 @@ class EmbeddingCache:
         if magic != cls._MAGIC or ver != 1:
             raise ValueError(f"{path}: not a scone_b200 cache file")
         cache = cls(n_gram_extractor, dim, cache_dir=cache_dir, use_memory_map=use_memory_map,
-                    quant=["fp16", "int8", "int4"][q], group_size=group, **kwargs)
+                    quant=["fp16", "int8", "int4", "fp32"][q], group_size=group, **kwargs)
         t = cache.table
         if (t.row_stride, t.scale_offset, t.num_rows) != (stride, soff, nrows):
             raise ValueError("file geometry does not match this vocabulary / build")
@@ -337,12 +391,14 @@ class EmbeddingCache:
         """The reference engine's own tensor (``engine.py:235-259``): mean of the rows of all f-grams containing each
         position, zeros where none.  Optional mode; :meth:`lookup` is the Algorithm-2 path."""
         from ..table import embed_mean_forward
+        self._not_on_sharded("assemble_mean")
         return embed_mean_forward(self.n_gram_extractor.device_index(self.device), self.table, input_ids, dtype)
 
     # ---- persistence (reference :183-243) ----------------------------------------------------------------------
     def save(self, path: str) -> None:
         """One ``.npy`` pickle like the reference, but carrying the packed table and its geometry
         (the reference's memmap backend cannot be reloaded: raw memmap written :84-89, ``np.load`` at :232)."""
+        self._not_on_sharded("save")
         t = self.table
         present = self._present.cpu().numpy()
         np.save(path, {

@@ -59,7 +59,8 @@ class HostPipeline:
         return self.out[slot], self.h_id[slot], self.h_len[slot]
 
     def submit(self, h_ids: torch.Tensor):
-        """Enqueue one batch (pinned int64 [B, L]); returns the oldest finished result once ``slots - 1`` batches are in flight."""
+        """Enqueue one batch (pinned int64 [B, L]); returns the oldest finished result once ``slots - 1`` batches are in flight.
+        The ids are read by an asynchronous copy: ``h_ids`` must stay untouched until this batch's result has been handed back."""
         if not h_ids.is_pinned() or h_ids.dtype != torch.int64 or h_ids.numel() != self.B * self.L or not h_ids.is_contiguous():
             raise ValueError("h_ids must be a contiguous pinned int64 host tensor of the pipeline's batch shape")
         _lib.check(_lib.load().scone_pipeline_submit(self._h, h_ids.data_ptr(), C.byref(self._slot)))
@@ -67,6 +68,13 @@ class HostPipeline:
         if len(self.inflight) >= max(1, self.n - 1):
             return self._result(self.inflight.pop(0))
         return None
+
+    def follow(self, stream: Optional[torch.cuda.Stream] = None) -> None:
+        """Order every batch submitted from now on behind the work already enqueued on ``stream`` (default: the current
+        stream).  The pipeline runs on its own three streams and is ordered against the caller only at construction, so
+        call this after updating anything it reads -- ``table.store`` / ``cache_embeddings`` / ``set_base_embedding``."""
+        st = stream if stream is not None else torch.cuda.current_stream(self.index.device)
+        _lib.check(_lib.load().scone_pipeline_follow(self._h, st.cuda_stream))
 
     def flush(self):
         """Results of everything still in flight, oldest first."""

@@ -150,6 +150,17 @@ class PeerShardedTable:
         self.local = CacheTable(max(cap, 1), dim, quant, group_size, self.device, storage=storage)
         self.ptr_table = torch.tensor(list(self._handle.buffer_ptrs), dtype=torch.int64, device=self.device)
         self.rows_owned = shard_rows(self.total_rows, self.rank, self.world)
+        self._views = {}
+
+    def shard_view(self, rank: int):
+        """Rank ``rank``'s shard as a CacheTable over its peer-mapped buffer (reads cross NVLink; ``rank == self.rank`` is
+        the local shard).  Valid after that rank's :meth:`publish`."""
+        if rank == self.rank:
+            return self.local
+        if rank not in self._views:
+            buf = self._handle.get_buffer(rank, tuple(self.local.storage.shape), torch.uint8)
+            self._views[rank] = self.local.view_of(buf)
+        return self._views[rank]
 
     def store_owned(self, rows_fp32: torch.Tensor, fgram_ids: torch.Tensor) -> None:
         """Quantise and store the rows of the given GLOBAL f-gram ids; ids this rank does not own are ignored."""
@@ -173,19 +184,15 @@ def embed_forward_sharded(index, table: PeerShardedTable, base_emb: torch.Tensor
     from . import _lib
     from .index import _stream_ptr
     from .table import _OUT
+    from .table import check_embed_args
     ids = index._check_ids(input_ids)
     B, L = ids.shape
     dev = index.device
-    D = table.local.dim
-    if base_emb.dtype not in (torch.bfloat16, torch.float16) or base_emb.dim() != 2 or base_emb.shape[1] != D \
-            or not base_emb.is_contiguous() or base_emb.device != dev:
-        raise ValueError(f"base_emb must be contiguous bf16/fp16 [V, {D}] on {dev}")
-    if out is None:
-        out = torch.empty((B, L, D), dtype=base_emb.dtype, device=dev)
-    if out_id is None:
-        out_id = torch.empty((B, L), dtype=torch.int32, device=dev)
-    if out_len is None:
-        out_len = torch.empty((B, L), dtype=torch.uint8, device=dev)
+    if table.device != dev:
+        raise ValueError("index and shard must be on the same device")
+    out, out_id, out_len = check_embed_args(dev, table.local.dim, base_emb, pos_emb, (B, L), out, out_id, out_len, True)
+    if status is not None and (status.device != dev or status.dtype != torch.int32):
+        raise ValueError("status must be an int32 tensor on the index device")
     with torch.cuda.device(dev):
         _lib.check(_lib.load().scone_embed_forward_sharded(
             index.handle, C.byref(table.local.desc), table.ptr_table.data_ptr(), table.world, table.total_rows,

@@ -23,7 +23,8 @@ def table_layout(quant: str, dim: int, group: int = 128, align: int = 32) -> Tup
 
 
 class CacheTable:
-    """N rows of D elements stored as FP16 / INT8 (per-row scale) / INT4 (per-group fp16 scales).
+    """N rows of D elements stored as FP32 (unquantised, the reference's own storage) / FP16 / INT8 (per-row scale) /
+    INT4 (per-group fp16 scales).
 
     Row r is the embedding of f-gram id r (reference ``scone/inference/embedding_cache.py:77,99``).
     ``storage`` is a uint8 tensor [N, row_stride]: on the GPU (tier "hbm") or pinned host memory
@@ -110,53 +111,75 @@ class CacheTable:
         return CacheTable(storage.shape[0], self.dim, self.quant, self.group, self.device, "hbm", storage=storage)
 
 
+def check_embed_args(dev: torch.device, dim: int, base_emb: torch.Tensor, pos_emb: Optional[torch.Tensor], shape: Tuple[int, ...],
+                     out: Optional[torch.Tensor], out_id: Optional[torch.Tensor] = None, out_len: Optional[torch.Tensor] = None,
+                     want_ids: bool = False):
+    """Argument checks shared by every fused entry (hbm, host, sharded tiers; resolved-ids gather): a short or mistyped
+    ``pos_emb`` / ``out`` would otherwise become an out-of-bounds bulk copy instead of a ValueError.  ``shape`` is the id
+    tensor's shape (its last dimension is the sequence length).  Allocates what is missing; returns (out, out_id, out_len)."""
+    L = shape[-1] if len(shape) else 1
+    n = 1
+    for d in shape:
+        n *= int(d)
+    if base_emb.dtype not in (torch.bfloat16, torch.float16):
+        raise ValueError("base_emb must be bf16 or fp16 (it defines the output dtype)")
+    if base_emb.device != dev:
+        raise ValueError("index, table and base_emb must be on the same device")
+    if base_emb.dim() != 2 or base_emb.shape[1] != dim or not base_emb.is_contiguous():
+        raise ValueError(f"base_emb must be contiguous [V, {dim}]")
+    if pos_emb is not None:
+        if pos_emb.dtype != base_emb.dtype or pos_emb.device != dev or not pos_emb.is_contiguous() \
+                or pos_emb.dim() != 2 or pos_emb.shape[1] != dim or pos_emb.shape[0] < L:
+            raise ValueError(f"pos_emb must be contiguous [>= {L}, {dim}] {base_emb.dtype} on {dev}")
+    if out is None:
+        out = torch.empty(tuple(shape) + (dim,), dtype=base_emb.dtype, device=dev)
+    elif out.dtype != base_emb.dtype or tuple(out.shape) != tuple(shape) + (dim,) or not out.is_contiguous() or out.device != dev:
+        raise ValueError(f"out must be contiguous {tuple(shape) + (dim,)} in base_emb.dtype on {dev}")
+    if want_ids:
+        if out_id is None:
+            out_id = torch.empty(tuple(shape), dtype=torch.int32, device=dev)
+        if out_len is None:
+            out_len = torch.empty(tuple(shape), dtype=torch.uint8, device=dev)
+        if out_id.dtype != torch.int32 or out_len.dtype != torch.uint8 or out_id.numel() != n or out_len.numel() != n \
+                or not out_id.is_contiguous() or not out_len.is_contiguous() or out_id.device != dev or out_len.device != dev:
+            raise ValueError("out_id must be contiguous int32 and out_len uint8, both of the id tensor's shape, on the index device")
+    else:
+        out_id = out_len = None
+    return out, out_id, out_len
+
+
 def embed_forward(index: FGramIndex, table: CacheTable, base_emb: torch.Tensor, input_ids: torch.Tensor,
                   pos_emb: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
                   status: Optional[torch.Tensor] = None, want_ids: bool = True,
-                  out_id: Optional[torch.Tensor] = None, out_len: Optional[torch.Tensor] = None, combine: str = "replace"):
+                  out_id: Optional[torch.Tensor] = None, out_len: Optional[torch.Tensor] = None, combine: str = "replace",
+                  inputs_stable: bool = False):
     """The fused hot path.  Returns (embeds [B, L, D] in base_emb.dtype, fgram_id int32 [B, L], match_len uint8 [B, L]).
 
     out[b, i] = dequant(table[fgram_id[b, i]]) if an f-gram ends at (b, i) else base_emb[input_ids[b, i]]
     (+ pos_emb[i] when given).  ``combine="add"`` is the reference code's combine instead of Algorithm 2's replacement
     (``scone/models/language_model.py:239-243``): base_emb[input_ids[b, i]] + dequant(row) where an f-gram ends.
     Everything is enqueued on the current stream; nothing synchronises.
+
+    ``inputs_stable=True`` (``SCONE_EMBED_INPUTS_STABLE``): the caller vouches that none of the inputs (ids, table, base /
+    position rows) is written by the kernel that precedes this call on the stream -- a serving loop whose ids arrive by
+    copy and whose tables are static.  Back-to-back lookups then overlap: the next call's matching and row fetches run
+    under this call's tail, only its writes wait.  Same results.
     """
     if combine not in ("replace", "add"):
         raise ValueError("combine must be 'replace' or 'add'")
     ids = index._check_ids(input_ids)
     B, L = ids.shape
     dev = index.device
-    if base_emb.device != dev or table.device != dev:
+    if table.device != dev:
         raise ValueError("index, table and base_emb must be on the same device")
-    if base_emb.dtype not in (torch.bfloat16, torch.float16):
-        raise ValueError("base_emb must be bf16 or fp16 (it defines the output dtype)")
-    if base_emb.dim() != 2 or base_emb.shape[1] != table.dim or not base_emb.is_contiguous():
-        raise ValueError(f"base_emb must be contiguous [V, {table.dim}]")
-    if pos_emb is not None:
-        if pos_emb.dtype != base_emb.dtype or pos_emb.device != dev or not pos_emb.is_contiguous() \
-                or pos_emb.dim() != 2 or pos_emb.shape[1] != table.dim or pos_emb.shape[0] < L:
-            raise ValueError(f"pos_emb must be contiguous [>= {L}, {table.dim}] {base_emb.dtype} on {dev}")
-    if out is None:
-        out = torch.empty((B, L, table.dim), dtype=base_emb.dtype, device=dev)
-    elif out.dtype != base_emb.dtype or tuple(out.shape) != (B, L, table.dim) or not out.is_contiguous() or out.device != dev:
-        raise ValueError("out must be contiguous [B, L, D] in base_emb.dtype")
-    if want_ids:
-        if out_id is None:
-            out_id = torch.empty((B, L), dtype=torch.int32, device=dev)
-        if out_len is None:
-            out_len = torch.empty((B, L), dtype=torch.uint8, device=dev)
-        if out_id.dtype != torch.int32 or out_len.dtype != torch.uint8 or out_id.numel() != B * L or out_len.numel() != B * L \
-                or not out_id.is_contiguous() or not out_len.is_contiguous() or out_id.device != dev or out_len.device != dev:
-            raise ValueError("out_id must be contiguous int32 [B, L] and out_len uint8 [B, L] on the index device")
-    else:
-        out_id = out_len = None
+    out, out_id, out_len = check_embed_args(dev, table.dim, base_emb, pos_emb, (B, L), out, out_id, out_len, want_ids)
+    opts = _lib.EmbedOpts((_lib.EMBED_ADDITIVE if combine == "add" else 0) | (_lib.EMBED_INPUTS_STABLE if inputs_stable else 0))
     with torch.cuda.device(dev):
-        entry = _lib.load().scone_embed_forward_additive if combine == "add" else _lib.load().scone_embed_forward
-        _lib.check(entry(
+        _lib.check(_lib.load().scone_embed_forward_ex(
             index.handle, C.byref(table.desc), base_emb.data_ptr(), base_emb.shape[0],
             pos_emb.data_ptr() if pos_emb is not None else None, ids.data_ptr(), B, L, out.data_ptr(), _OUT[base_emb.dtype],
             out_id.data_ptr() if want_ids else None, out_len.data_ptr() if want_ids else None,
-            status.data_ptr() if status is not None else None, _stream_ptr(dev)))
+            status.data_ptr() if status is not None else None, C.byref(opts), _stream_ptr(dev)))
     return out, out_id, out_len
 
 
@@ -170,10 +193,13 @@ def embed_gather(table: CacheTable, base_emb: torch.Tensor, input_ids: torch.Ten
     if ids.dtype != torch.int64 or fid.dtype != torch.int32 or ids.shape != fid.shape:
         raise ValueError("input_ids (long) and fgram_id (int32) must have the same shape")
     dev = table.device
+    if ids.device != dev or fid.device != dev:
+        raise ValueError(f"input_ids and fgram_id must be on the table's device {dev}")
+    if status is not None and (status.device != dev or status.dtype != torch.int32):
+        raise ValueError("status must be an int32 tensor on the table's device")
     T = ids.numel()
     L = ids.shape[-1] if ids.dim() >= 1 else 1
-    if out is None:
-        out = torch.empty(tuple(ids.shape) + (table.dim,), dtype=base_emb.dtype, device=dev)
+    out, _, _ = check_embed_args(dev, table.dim, base_emb, pos_emb, tuple(ids.shape), out)
     with torch.cuda.device(dev):
         _lib.check(_lib.load().scone_embed_gather(
             C.byref(table.desc), base_emb.data_ptr(), base_emb.shape[0], pos_emb.data_ptr() if pos_emb is not None else None,

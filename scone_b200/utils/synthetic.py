@@ -164,13 +164,13 @@ def pack_table_numpy(quant: str, payload: np.ndarray, scales: Optional[np.ndarra
     Returns (packed uint8 [N, row_stride], row_stride, scale_offset)."""
     N = payload.shape[0]
     pb = np.ascontiguousarray(payload).view(np.uint8).reshape(N, -1)
-    if quant == "fp16":
+    if quant in ("fp16", "fp32"):
         sb = np.zeros((N, 0), dtype=np.uint8)
     elif quant == "int8":
         sb = np.ascontiguousarray(scales, dtype=np.float32).reshape(N, 1).view(np.uint8)
     else:
         sb = np.ascontiguousarray(scales, dtype=np.float16).view(np.uint8).reshape(N, -1)
-    scale_off = pb.shape[1] if quant != "fp16" else 0
+    scale_off = pb.shape[1] if quant in ("int8", "int4") else 0
     used = pb.shape[1] + sb.shape[1]
     stride = (used + align - 1) // align * align
     out = np.zeros((N, stride), dtype=np.uint8)

@@ -73,6 +73,25 @@ dist.barrier()
 good3 = np.array_equal(emb3.view(torch.int16).cpu().numpy().view(np.uint16), want) and np.array_equal(fid3.cpu().numpy(), wid)
 print(f"rank {rank}/{world} EmbeddingCache(tier='sharded'): {'OK' if good3 else 'MISMATCH'}", flush=True)
 ok = ok and good3
+# the reference-API methods take GLOBAL f-gram ids on every rank: rows of other ranks are read through their peer-mapped shard
+pick = np.random.default_rng(5 + rank).integers(0, N, size=64)
+want_rows = tab.rows_fp32(pick)
+got_rows = cache.get_embeddings(pick.tolist()).numpy()
+te = cache.get_token_embeddings(q[0, :64].tolist())
+g2i = {tuple(int(t) for t in toks[i, :lens[i]]): i for i in range(N)}
+tf = po.token_f_grams(g2i.keys(), max_n, q[0, :64].tolist())
+good4 = np.array_equal(got_rows, want_rows) and np.array_equal(cache.embeddings[int(pick[0])], want_rows[0]) \
+    and all(np.array_equal(te[p_].numpy(), tab.rows_fp32(np.array([g2i[g] for g in gr]))) for p_, gr in tf.items() if gr) \
+    and sorted(te) == sorted(p_ for p_, gr in tf.items() if gr)
+for what in ("save", "save_binary", "assemble_mean"):
+    try:
+        getattr(cache, what)("/tmp/should_not_exist") if what != "assemble_mean" else cache.assemble_mean(torch.from_numpy(q).to(dev))
+        good4 = False
+    except NotImplementedError:
+        pass
+dist.barrier()
+print(f"rank {rank}/{world} sharded get_embeddings / embeddings[] / get_token_embeddings: {'OK' if good4 else 'MISMATCH'}", flush=True)
+ok = ok and good4
 flag = torch.tensor([0 if ok else 1], device=dev)
 dist.all_reduce(flag)
 dist.destroy_process_group()

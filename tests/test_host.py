@@ -23,14 +23,14 @@ def test_library_loads_and_exports_every_declared_symbol():
     for name in declared:
         assert getattr(L, name) is not None
     assert L.scone_version() == _lib.ABI_VERSION == int(re.search(r"#define SCONE_B200_VERSION (\d+)", header).group(1))
-    assert ctypes.sizeof(_lib.TableDesc) == 40 and ctypes.sizeof(_lib.IndexInfo) == 48
+    assert ctypes.sizeof(_lib.TableDesc) == 40 and ctypes.sizeof(_lib.IndexInfo) == 48 and ctypes.sizeof(_lib.EmbedOpts) == 16
 
 
 def test_table_layout_matches_oracle_packing():
     from scone_b200 import table_layout
     from scone_b200.utils.synthetic import pack_table_numpy
     rows = (np.random.default_rng(0).standard_normal((4, 1024)) * 0.02).astype(np.float32)
-    for quant, want in (("fp16", (2048, 0)), ("int8", (1056, 1024)), ("int4", (544, 512))):
+    for quant, want in (("fp32", (4096, 0)), ("fp16", (2048, 0)), ("int8", (1056, 1024)), ("int4", (544, 512))):
         assert table_layout(quant, 1024) == want
         t = po.OracleTable.from_fp32(rows, quant)
         _, stride, soff = pack_table_numpy(quant, t.payload, t.scales)
@@ -217,6 +217,7 @@ def test_c_abi_rejects_bad_arguments_without_a_gpu():
     rs, so = C.c_int64(), C.c_int32()
     assert L.scone_table_layout(1, 1024, 128, 0, C.byref(rs), C.byref(so)) == 0 and (rs.value, so.value) == (1056, 1024)
     assert L.scone_table_layout(2, 4096, 128, 128, C.byref(rs), C.byref(so)) == 0 and (rs.value, so.value) == (2176, 2048)
+    assert L.scone_table_layout(3, 1024, 128, 0, C.byref(rs), C.byref(so)) == 0 and (rs.value, so.value) == (4096, 0)   # SCONE_QUANT_FP32
     assert L.scone_table_layout(7, 1024, 128, 0, C.byref(rs), C.byref(so)) == _lib.E_INVALID
     assert L.scone_table_layout(2, 1000, 128, 0, C.byref(rs), C.byref(so)) == _lib.E_INVALID
     h = C.c_void_p()
@@ -225,6 +226,10 @@ def test_c_abi_rejects_bad_arguments_without_a_gpu():
     assert L.scone_index_create(None, None, 5, 3, 0.95, None, C.byref(h)) == _lib.E_INVALID       # load factor
     assert L.scone_index_lookup(None, None, 1, 1, None, None, None) == _lib.E_INVALID
     assert L.scone_index_destroy(None) == 0 and L.scone_pipeline_destroy(None) == 0
+    assert L.scone_pipeline_follow(None, None) == _lib.E_INVALID
+    opts = _lib.EmbedOpts(0x80)                                                                   # unknown flag bit
+    assert L.scone_embed_forward_ex(None, None, None, 0, None, None, 1, 1, None, 0, None, None, None, C.byref(opts), None) == _lib.E_INVALID
+    assert b"flag" in L.scone_last_error()
     desc = _lib.TableDesc(16, 100, 4, 1, 1024, 128, 1024)                                         # row_stride 100: not a multiple of 16
     assert L.scone_table_gather(C.byref(desc), None, 1, None, 2, None, None) == _lib.E_INVALID
 
@@ -283,7 +288,7 @@ def test_bench_byte_accounting_matches_the_survey_formula():
     spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
     b = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(b)
-    assert b.row_bytes_algorithmic("fp16", 768) == 1536
+    assert b.row_bytes_algorithmic("fp16", 768) == 1536 and b.row_bytes_algorithmic("fp32", 768) == 3072
     assert b.row_bytes_algorithmic("int8", 1024) == 1028
     assert b.row_bytes_algorithmic("int4", 4096) == 2112
     w2, w3 = b.WORKLOADS["config2"], b.WORKLOADS["config3"]

@@ -144,6 +144,9 @@ def test_gather_and_half_cast_golden():
     bits = po.cast_bits(tab.rows_fp32(z["pick"]), "fp16")
     assert np.array_equal(bits, z["half_bits"])                          # engine.py:265-266 `.half()`
     assert np.array_equal(po.f32_to_f16_bits(z["gathered"]), z["half_bits"])
+    # the unquantised format is the reference's own storage: gathered rows are the fixture bit for bit
+    t32 = po.OracleTable.from_fp32(z["rows"], "fp32")
+    assert np.array_equal(t32.rows_fp32(z["pick"]).view(np.uint32), z["gathered"].view(np.uint32))
 
 
 def test_assemble_mean_golden():
@@ -151,6 +154,16 @@ def test_assemble_mean_golden():
     g2i = vocab_dict(z["vocab_tokens"], z["vocab_lens"])
     got = po.assemble_mean(g2i, int(z["max_n"]), lambda ids: z["rows"][ids], z["query"].tolist(), z["rows"].shape[1])
     np.testing.assert_allclose(got, z["assembled"], rtol=0, atol=1e-7)
+    assert np.array_equal(got.view(np.uint32), z["assembled"].view(np.uint32))     # the engine's tensor, bit for bit
+    # ... and so is the kernel's arithmetic (csrc/table.cu mean_kernel): fp32 running sum in list order, one divide
+    tf = po.token_f_grams(g2i.keys(), int(z["max_n"]), z["query"].tolist())
+    seq = np.zeros_like(got)
+    for pos, grams in tf.items():
+        acc = np.zeros(got.shape[1], np.float32)
+        for g in grams:
+            acc = (acc + z["rows"][g2i[g]]).astype(np.float32)
+        seq[pos] = (acc / np.float32(len(grams))).astype(np.float32) if len(grams) > 1 else acc
+    assert np.array_equal(seq.view(np.uint32), z["assembled"].view(np.uint32))
 
 
 def test_bf16_f16_casts_against_torch_and_c():
@@ -200,7 +213,7 @@ def test_quant_formulas_properties():
     assert np.array_equal(po.unpack_int4(p)[:, 0::2], (p & 0xF).astype(np.int8) - 8)
 
 
-@pytest.mark.parametrize("quant", ["fp16", "int8", "int4"])
+@pytest.mark.parametrize("quant", ["fp32", "fp16", "int8", "int4"])
 @pytest.mark.parametrize("out_dtype", ["bf16", "fp16"])
 def test_embed_forward_py_vs_c(quant, out_dtype):
     from scone_b200.utils.synthetic import pack_table_numpy

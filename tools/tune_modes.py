@@ -3,7 +3,8 @@
 
     python tools/tune_modes.py config2 "mode;ENV=val,ENV=val" ...
 
-mode in {replace, pos, add, addpos}.  Overrides understood by the SCONE_TUNE build: SCONE_EMBED_VARIANT=kind:U:NM:NG:MINB:KB,
+mode in {replace, pos, add, addpos}; STABLE=1 among the overrides passes SCONE_EMBED_INPUTS_STABLE (SCONE_NO_EARLY=1 makes the
+library ignore it: read once at load time, so use STABLE for A/Bs inside one process).  Overrides understood by the SCONE_TUNE build: SCONE_EMBED_VARIANT=kind:U:NM:NG:MINB:KB,
 SCONE_EMBED_P (lanes per position), SCONE_STAGGER_NS / SCONE_STAGGER_CTA_NS, SCONE_HINT (what-if: perfect pre-filter).
 """
 import json
@@ -56,7 +57,9 @@ def main():
         for kv in filter(None, envs.split(",")):
             k, _, v = kv.partition("=")
             os.environ[k] = v
-        kw = dict(pos_emb=pos if mode in ("pos", "addpos") else None, combine="add" if mode in ("add", "addpos") else "replace")
+        stable = os.environ.pop("STABLE", "0") == "1"
+        kw = dict(pos_emb=pos if mode in ("pos", "addpos") else None, combine="add" if mode in ("add", "addpos") else "replace",
+                  inputs_stable=stable)
         fn = lambda k: sb.embed_forward(index, table, base, batches[k % 8], out=out, out_id=out_id, out_len=out_len, **kw)  # noqa: E731
         ms = graph_time(fn)
         # every override must reproduce the default build's bits for the same mode
