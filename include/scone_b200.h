@@ -133,6 +133,18 @@ int scone_table_layout(int32_t quant, int32_t dim, int32_t group, int32_t align,
 int scone_table_store(const scone_table_desc_t *table, const float *d_rows_f32, const int64_t *d_row_ids,
                       int64_t row_base, int64_t k, void *stream);
 
+/* cache_embeddings with the reference's bias-free `f_gram_projection` (scone/models/language_model.py:172-176, applied at
+ * :236 on every forward pass) folded into the table build:  table[row r] = quantise(d_rows[r, :] @ d_proj^T).
+ * d_rows_bf16: bf16 [k, in_dim] (the f-gram model's output rows), d_proj_bf16: bf16 [dim, in_dim] (nn.Linear weight layout:
+ * out_features x in_features), both row-major, 16-byte aligned, in_dim a multiple of 8; table->dim a multiple of 64.
+ * A tcgen05 / TMEM GEMM (bf16 x bf16 -> fp32) whose epilogue IS the quantise-and-store of scone_table_store: the fp32
+ * [k, dim] product is never written to memory.  Rows go to d_row_ids[0..k) (NULL -> row_base ..); destinations outside the
+ * table are skipped and counted in *d_bad (may be NULL).  Result: the fp32 product of the bf16 inputs (fp32 accumulation in
+ * tensor-core order) through exactly the quantiser of scone_table_store. */
+int scone_table_store_projected(const scone_table_desc_t *table, const void *d_rows_bf16, const void *d_proj_bf16,
+                                int32_t in_dim, const int64_t *d_row_ids, int64_t row_base, int64_t k,
+                                uint32_t *d_bad, void *stream);
+
 /* get_embeddings (embedding_cache.py:113-147): out[r] = dequant(table[d_row_ids[r]]) as
  * out_dtype ([k, D] contiguous).  Row ids outside [0, num_rows) produce a zero row and set
  * bit SCONE_STATUS_TOKEN_OOR in *d_status when d_status is not NULL. */

@@ -23,7 +23,7 @@ E_INVALID, E_CUDA, E_VOCAB, E_NOMEM = -1, -2, -3, -4
 SYMBOLS = [
     "scone_version", "scone_last_error", "scone_launch_count", "scone_host_gather_rows",
     "scone_index_create", "scone_index_destroy", "scone_index_info", "scone_index_lookup", "scone_index_match_all",
-    "scone_table_layout", "scone_table_store", "scone_table_gather", "scone_table_gather_packed",
+    "scone_table_layout", "scone_table_store", "scone_table_store_projected", "scone_table_gather", "scone_table_gather_packed",
     "scone_embed_forward", "scone_embed_forward_additive", "scone_embed_forward_ex", "scone_embed_gather", "scone_embed_forward_sharded", "scone_embed_mean_forward",
     "scone_pipeline_create", "scone_pipeline_submit", "scone_pipeline_follow", "scone_pipeline_wait", "scone_pipeline_destroy",
 ]
@@ -76,6 +76,7 @@ def load() -> C.CDLL:
     L.scone_index_match_all.argtypes = [vp, vp, i64, i64, vp, vp]
     L.scone_table_layout.argtypes = [i32, i32, i32, i32, C.POINTER(i64), C.POINTER(i32)]
     L.scone_table_store.argtypes = [C.POINTER(TableDesc), vp, vp, i64, i64, vp]
+    L.scone_table_store_projected.argtypes = [C.POINTER(TableDesc), vp, vp, i32, vp, i64, i64, vp, vp]
     L.scone_table_gather.argtypes = [C.POINTER(TableDesc), vp, i64, vp, i32, vp, vp]
     L.scone_table_gather_packed.argtypes = [C.POINTER(TableDesc), vp, i64, vp, vp, vp]
     L.scone_host_gather_rows.argtypes = [vp, i64, i64, vp, i64, vp, i32]

@@ -16,7 +16,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB_DIR = os.path.join(PKG, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libscone_b200.so")
-SOURCES = ["api.cu", "index.cu", "table.cu", "embed.cu", "pipeline.cu"]
+SOURCES = ["api.cu", "index.cu", "table.cu", "embed.cu", "pipeline.cu", "fold.cu"]
 # the fused path's kernels are compiled once per (table format, output type): eight translation units, in parallel
 INST_SOURCE = "embed_inst.cu"
 INSTANCES = [(q, o) for o in (0, 1) for q in (0, 1, 2, 3)]

@@ -146,8 +146,15 @@ class EmbeddingCache:
 
     # ---- reference API --------------------------------------------------------------------------------
     def cache_embeddings(self, f_gram_ids: Union[List[int], Dict[int, torch.Tensor]],
-                         embeddings: Optional[torch.Tensor] = None, verbose: bool = True) -> None:
+                         embeddings: Optional[torch.Tensor] = None, verbose: bool = True,
+                         projection: Optional[torch.Tensor] = None) -> None:
         """Store rows (reference :56-111).  Rows are quantised on the GPU, in chunks, straight into the table.
+
+        ``projection`` ([embedding_dim, H_f], the ``nn.Linear.weight`` of the reference's bias-free ``f_gram_projection``,
+        ``language_model.py:172-176``): ``embeddings`` is then ``[k, H_f]`` -- the f-gram model's own output -- and the table
+        receives ``embeddings @ projection.T``, computed on the tensor cores with the quantise-and-store as the GEMM's
+        epilogue, so that ``lookup`` serves rows already in the model's hidden size (the reference projects on every
+        forward pass, ``:236``).
 
         Accepts the reference signature ``(f_gram_ids, embeddings[k, D])`` and also the ``{id: row}`` dict
         that the reference's own tests and scripts pass (tests/test_embedding_cache.py:78).
@@ -164,8 +171,11 @@ class EmbeddingCache:
         if embeddings is None:
             raise ValueError("embeddings required")
         embeddings = torch.as_tensor(embeddings)
-        if embeddings.dim() != 2 or embeddings.shape[1] != self.embedding_dim or embeddings.shape[0] != len(ids):
-            raise ValueError(f"embeddings must be [{len(ids)}, {self.embedding_dim}]")
+        width = self.embedding_dim if projection is None else projection.shape[1]
+        if projection is not None and (projection.dim() != 2 or projection.shape[0] != self.embedding_dim):
+            raise ValueError(f"projection must be [{self.embedding_dim}, H_f]")
+        if embeddings.dim() != 2 or embeddings.shape[1] != width or embeddings.shape[0] != len(ids):
+            raise ValueError(f"embeddings must be [{len(ids)}, {width}]")
         table = self.table
         if isinstance(ids, range):
             id_t = torch.arange(ids.start, ids.stop, ids.step, dtype=torch.int64, device=self.device)
@@ -174,6 +184,14 @@ class EmbeddingCache:
         if len(ids) and (int(id_t.min()) < 0 or int(id_t.max()) >= len(self.n_gram_extractor)):
             raise IndexError("f-gram id out of range")                                     # memmap backend: IndexError
         self._missing = None
+        if projection is not None:
+            if self.tier != "hbm":
+                raise ValueError("projection folding is available for the hbm tier")
+            chunk = max(1, (256 << 20) // (4 * width))
+            for s in range(0, len(ids), chunk):
+                table.store_projected(embeddings[s:s + chunk], projection, id_t[s:s + chunk])
+            self._present[id_t] = True
+            return
         if self.tier == "sharded":
             # every rank may be handed every row; each keeps the ones it owns.  Call publish() after the last store.
             self._sharded.store_owned(embeddings.to(torch.float32), id_t)

@@ -84,6 +84,34 @@ class CacheTable:
             _lib.check(_lib.load().scone_table_store(C.byref(self.desc), rows.data_ptr(), ids_ptr, int(row_base), k,
                                                      _stream_ptr(self.device)))
 
+    def store_projected(self, rows: torch.Tensor, projection: torch.Tensor, row_ids: Optional[torch.Tensor] = None,
+                        row_base: int = 0) -> None:
+        """``table[row] = quantise(rows @ projection.T)`` -- the reference's bias-free ``f_gram_projection``
+        (``scone/models/language_model.py:172-176, 236``) folded into the table build.  rows [k, H_f], projection [D, H_f]
+        (``nn.Linear.weight`` layout); both are rounded to bf16 (RNE) and multiplied on the tensor cores with fp32
+        accumulation; the quantise-and-store of :meth:`store` is the GEMM's epilogue (no fp32 [k, D] intermediate)."""
+        _require_cuda(rows, "rows")
+        _require_cuda(projection, "projection")
+        if rows.dim() != 2 or projection.dim() != 2 or projection.shape[0] != self.dim or rows.shape[1] != projection.shape[1]:
+            raise ValueError(f"rows must be [k, H_f] and projection [{self.dim}, H_f]")
+        if self.tier != "hbm":
+            raise ValueError("store_projected writes an HBM-resident table")
+        a = rows.to(device=self.device, dtype=torch.bfloat16).contiguous()
+        w = projection.detach().to(device=self.device, dtype=torch.bfloat16).contiguous()
+        k = a.shape[0]
+        ids_ptr = None
+        if row_ids is not None:
+            row_ids = row_ids.to(device=self.device, dtype=torch.int64).contiguous()
+            if row_ids.numel() != k:
+                raise ValueError("row_ids and rows disagree on k")
+            ids_ptr = row_ids.data_ptr()
+        bad = torch.zeros((1,), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().scone_table_store_projected(C.byref(self.desc), a.data_ptr(), w.data_ptr(), int(a.shape[1]), ids_ptr,
+                                                               int(row_base), k, bad.data_ptr(), _stream_ptr(self.device)))
+        if int(bad.item()):
+            raise IndexError("row id out of range")
+
     def gather(self, row_ids: torch.Tensor, dtype: torch.dtype = torch.float32) -> torch.Tensor:
         """dequant(table[row_ids]) -> [k, D] (the reference's get_embeddings gather)."""
         row_ids = row_ids.to(device=self.device, dtype=torch.int64).contiguous()

@@ -944,3 +944,54 @@ def test_sharded_tier_two_gpus_reference_api(tmp_path):
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
     assert "MISMATCH" not in p.stdout and p.stdout.count("OK") >= 8
+
+
+@pytest.mark.parametrize("Hf,H,k", [(384, 768, 1000), (768, 1024, 517), (96, 256, 300), (1024, 4096, 260)])
+def test_projection_fold(Hf, H, k):
+    """table[row] = quantise(rows @ W^T): the reference's bias-free f_gram_projection (language_model.py:172-176, :236) folded
+    into the table build by a tcgen05 / TMEM GEMM whose epilogue is the quantiser.
+    (1) the unquantised result against the exact product of the bf16-rounded inputs, within the accumulation-order bound of
+        oracle/py_oracle.py::fold_projection;
+    (2) every quantised format bit-identical to scone_table_store (the oracle-pinned quantiser) applied to (1): the epilogue IS
+        that quantiser;
+    (3) so the dequantised rows are within half a quantisation step (+ the bound) of the exact product."""
+    sb, S = _mods()
+    rng = np.random.default_rng(Hf + H)
+    rows = (rng.standard_normal((k, Hf)) * 0.5).astype(np.float32)
+    W = (rng.standard_normal((H, Hf)) * (1.0 / np.sqrt(Hf))).astype(np.float32)
+    rows[3] = 0.0                                   # an all-zero row: scale 1
+    P, bound = po.fold_projection(rows, W)
+    perm = rng.permutation(k)
+    t32 = sb.CacheTable(k, H, "fp32")
+    t32.store_projected(torch.from_numpy(rows).to(DEV), torch.from_numpy(W).to(DEV), row_ids=torch.from_numpy(perm).to(DEV))
+    x = t32.gather(torch.arange(k, device=DEV)).cpu().numpy()
+    x_src = x[perm]                                 # row r of the input went to table row perm[r]
+    assert np.all(np.abs(x_src - P) <= bound + 1e-30), float(np.max(np.abs(x_src - P) - bound))
+    assert np.array_equal(x_src[3], np.zeros(H, np.float32))
+    for quant in ("fp16", "int8", "int4"):
+        tq = sb.CacheTable(k, H, quant)
+        tq.store_projected(torch.from_numpy(rows).to(DEV), torch.from_numpy(W).to(DEV), row_ids=torch.from_numpy(perm).to(DEV))
+        ref = sb.CacheTable(k, H, quant)
+        ref.store(torch.from_numpy(x).to(DEV))
+        assert torch.equal(tq.storage, ref.storage), quant
+        dq = tq.gather(torch.arange(k, device=DEV)).cpu().numpy()[perm]
+        if quant == "fp16":
+            step = np.maximum(np.abs(P) * 2.0 ** -10, 2.0 ** -24)
+        elif quant == "int8":
+            step = (np.abs(P).max(axis=1, keepdims=True) / 127.0) * np.ones_like(P)
+        else:
+            step = np.repeat((np.abs(P).reshape(k, H // 128, 128).max(axis=2) / 7.0).astype(np.float16).astype(np.float32), 128, axis=1)
+        assert np.all(np.abs(dq - P) <= 0.51 * step + 4 * bound + 1e-30), quant
+    # the drop-in entry: cache_embeddings(..., projection=W) then lookup serves the projected rows
+    toks, lens = S.make_vocab_numpy(k, 3, 200, seed=5)
+    ex = sb.NGramExtractor.from_arrays(toks, lens)
+    cache = sb.EmbeddingCache(ex, H, quant="fp16", out_dtype=torch.float16)
+    cache.cache_embeddings(list(range(k)), torch.from_numpy(rows), verbose=False, projection=torch.from_numpy(W))
+    got = cache.get_embeddings(list(range(k))).numpy()
+    ref16 = sb.CacheTable(k, H, "fp16")
+    t_id = sb.CacheTable(k, H, "fp32")
+    t_id.store_projected(torch.from_numpy(rows).to(DEV), torch.from_numpy(W).to(DEV))
+    ref16.store(t_id.gather(torch.arange(k, device=DEV)))
+    assert np.array_equal(got, ref16.gather(torch.arange(k, device=DEV)).cpu().numpy())
+    with pytest.raises(ValueError):
+        cache.cache_embeddings([0], torch.zeros(1, Hf), projection=torch.zeros(H + 64, Hf))
