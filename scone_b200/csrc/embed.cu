@@ -46,6 +46,18 @@ static int dispatch(int P, EmbedParams &p, int quant, int out_dtype, cudaStream_
     if (const char *e = getenv("SCONE_STAGGER_CTA_NS")) p.stagger_cta_ns = atoi(e);
 #endif
     if (p.additive && P < 4) P = 4;  // see launch_p
+    // SCONE_EMBED_PIPE=0 selects embed_bulk_kernel (one ring, the matcher stages its own tile) instead of the three-role
+    // pipeline of embed_pipe.cuh; read per call so that the tests can run both.
+    const char *pe = getenv("SCONE_EMBED_PIPE");
+    if (!pe || pe[0] != '0') p.flags |= kEmbedPipe;
+    if (p.flags & kEmbedPipe) {
+        // full-size tiles on any shape before smaller tiles: the pipeline's matchers do not depend on the row ring
+        const int pn[] = {kNarrow6, kMid, kWide, kSmall}, pw[] = {kWide, kSmall};
+        const int *po = moved >= 6144 ? pw : pn;
+        const int n_po = moved >= 6144 ? 2 : 4;
+        for (int pp = P; pp <= 8 && rc == kNoFit; pp <<= 1)
+            for (int s = 0; s < n_po && rc == kNoFit; ++s) rc = dispatch_one(pp, p, quant, out_dtype, stream, po[s]);
+    }
     for (int s = 0; s < n_order && rc == kNoFit; ++s)
         for (int pp = P; pp <= 8 && rc == kNoFit; pp <<= 1) {
             rc = dispatch_one(pp, p, quant, out_dtype, stream, order[s]);

@@ -76,6 +76,7 @@ __device__ __forceinline__ const uint8_t *row_ptr(const EmbedParams &p, int32_t 
 }
 
 constexpr int kRing = 16;  // tiles the matchers may run ahead of the gather warps
+constexpr uint32_t kEmbedPipe = 1u << 31;  // EmbedParams::flags, internal: use embed_pipe_kernel instead of embed_bulk_kernel
 
 // programmatic dependent launch: block until the grid this one was launched behind has completed and its writes are visible
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
@@ -579,6 +580,10 @@ __global__ void __launch_bounds__(32 * (NM + NG), MINB) embed_bulk_kernel(const 
 }
 
 
+}  // namespace scone
+#include "embed_pipe.cuh"
+namespace scone {
+
 static int num_sms() {
     static int n = 0;
     if (n == 0) {
@@ -673,6 +678,23 @@ static int launch_bulk(EmbedParams &p, const BulkLayout &lay, cudaStream_t strea
     return launch_pdl(kern, blocks, 32 * (NM + NG), (size_t)lay.smem_bytes, stream, p, lay);
 }
 
+template <int QUANT, int OUT, int P, int NM, int NG, int MINB, bool ADD>
+static int launch_pipe(EmbedParams &p, const PipeLayout &lay, cudaStream_t stream) {
+    constexpr int G = 32 / P;
+    auto kern = embed_pipe_kernel<QUANT, OUT, P, NM, NG, MINB, ADD>;
+    static int configured[64] = {0};  // per device: the attribute lives in the device's context
+    int dev = 0;
+    SCONE_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || configured[dev] < lay.smem_bytes) {
+        SCONE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.smem_bytes));
+        if (dev >= 0 && dev < 64) configured[dev] = lay.smem_bytes;
+    }
+    p.num_tiles = (p.T + G - 1) / G;
+    const int64_t resident = (int64_t)num_sms() * MINB;
+    const unsigned blocks = (unsigned)(p.num_tiles < resident ? p.num_tiles : resident);
+    return launch_pdl(kern, blocks, 32 * (NM + 1 + NG), (size_t)lay.smem_bytes, stream, p, lay);
+}
+
 // Kernel selection (measured on B200, profiles/tune_r01.md).  Rows that fit a shared-memory ring go through the
 // bulk-copy variant; its shape follows the traffic per position:
 //   kNarrow6  < 6 KB moved, tiny rows : 6 matcher + 4 gather warps, 3 CTAs/SM, 70 KB ring  (needs >= 6 ring slots)
@@ -720,6 +742,32 @@ static int launch(EmbedParams &p, cudaStream_t stream, int shape) {
         if (v.kind == 0) return launch_ldg<QUANT, OUT, P, 4, 2, 6, 4>(p, stream);
     }
 #endif
+    if (p.flags & kEmbedPipe) {
+        // three-role pipeline (embed_pipe.cuh): tiles keep their full size, the row ring only needs two slots
+        PipeLayout pl;
+        switch (shape) {
+            case kNarrow6:
+            case kNarrow4:
+                if (pipe_layout(p, G, 5, 70 * 1024, pl)) {
+                    set_stagger<P, 5, 3>(p);
+                    return launch_pipe<QUANT, OUT, P, 5, 4, 3, ADD>(p, pl, stream);
+                }
+                return kNoFit;
+            case kMid:
+                if (pipe_layout(p, G, 4, 100 * 1024, pl)) return launch_pipe<QUANT, OUT, P, 4, 8, 2, ADD>(p, pl, stream);
+                return kNoFit;
+            case kWide:
+            case kWide3:
+            case kWide2:
+                if (pipe_layout(p, G, 6, 200 * 1024, pl)) return launch_pipe<QUANT, OUT, P, 6, 12, 1, ADD>(p, pl, stream);
+                return kNoFit;
+            case kSmall:
+                if (pipe_layout(p, G, 2, 70 * 1024, pl)) return launch_pipe<QUANT, OUT, P, 2, 6, 3, ADD>(p, pl, stream);
+                return kNoFit;
+            default:
+                return launch_ldg<QUANT, OUT, P, 4, 2, 6, 4>(p, stream);
+        }
+    }
     switch (shape) {
         case kNarrow6:
             if (bulk_layout(p, G, 6, 70 * 1024, lay)) {

@@ -21,14 +21,16 @@ DEV = "cuda"
 @pytest.fixture(autouse=True, params=["auto", "wide"])
 def index_format(request, monkeypatch):
     """Every test runs twice: with the library defaults (compact 16-byte slots whenever the tokens allow; the Bloom
-    pre-filter consulted by large batches only), and with the 32-byte slot format forced and the pre-filter consulted
-    for every batch size."""
+    pre-filter consulted by large batches only; the three-role pipeline kernel of embed_pipe.cuh), and with the 32-byte slot
+    format forced, the pre-filter consulted for every batch size and the single-ring kernel (embed_bulk_kernel) selected."""
     if request.param == "wide":
         monkeypatch.setenv("SCONE_INDEX_FORMAT", "wide")
         monkeypatch.setenv("SCONE_INDEX_FILTER", "always")
+        monkeypatch.setenv("SCONE_EMBED_PIPE", "0")
     else:
         monkeypatch.delenv("SCONE_INDEX_FORMAT", raising=False)
         monkeypatch.delenv("SCONE_INDEX_FILTER", raising=False)
+        monkeypatch.delenv("SCONE_EMBED_PIPE", raising=False)
     return request.param
 
 
