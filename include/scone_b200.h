@@ -67,8 +67,11 @@ typedef struct scone_index_info {
     int32_t max_n;
     uint32_t len_mask;   /* bit (n-1) set when some f-gram has length n */
     int32_t max_probe;   /* longest insert probe sequence seen at build time */
-    int32_t slot_bytes;  /* 32, or 16 for the compact format (all tokens < 65535 and max_n <= 6) */
+    int32_t slot_bytes;  /* 32, or 16 for the compact formats (all tokens < 65535 and max_n <= 6; or all tokens < 1048575,
+                            max_n <= 5 and fewer than 2^28 - 1 f-grams) */
     int64_t filter_bytes; /* bytes of the L2-resident pre-filter (included in `bytes`), 0 = none */
+    int32_t slot_format;  /* 0 = 32-byte slots, 1 = compact 16-byte (six 16-bit tokens), 2 = compact 16-byte (five 20-bit tokens) */
+    int32_t reserved;
 } scone_index_info_t;
 
 /* Where the cache rows live and how they are encoded.  Row r starts at
@@ -119,6 +122,21 @@ int scone_index_lookup(const scone_index_t *index, const int64_t *d_ids, int64_t
  * the per-position "all f-grams containing the token" lists are a re-indexing of it. */
 int scone_index_match_all(const scone_index_t *index, const int64_t *d_ids, int64_t B, int64_t L,
                           int32_t *d_out, void *stream);
+
+/* NGramExtractor.fit on the device (scone/tokenization/n_gram_extractor.py:72-104): count every n-gram (n = 1..max_n, never
+ * across texts) of a tokenised corpus, keep the max_f_grams most frequent (ties: first seen in the reference's enumeration
+ * order text -> n -> start, :91), THEN drop counts below min_freq (:92-94); id = rank (:98-99).
+ * d_tokens int32 [num_tokens] = the texts back to back, d_text_offsets int64 [num_texts + 1].  Output, in id order:
+ * d_out_tokens int32 [max_f_grams, max_n] (-1 padded), d_out_lens uint8 [max_f_grams], optional d_out_counts int64; *out_n =
+ * number of f-grams written, *out_distinct = distinct n-grams in the corpus (may be NULL).
+ * n-gram occurrences are hashed (64 bits, `seed`), radix-sorted and run-length counted; every run is verified to hold a single
+ * n-gram -- if two n-grams share a hash the call fails with SCONE_E_VOCAB and the caller retries with another seed.
+ * Synchronises the stream (it returns counts); scratch is allocated with cudaMallocAsync (32 bytes per n-gram occurrence);
+ * at most 2^31 - 1 occurrences per call. */
+int scone_fit_vocab(const int32_t *d_tokens, int64_t num_tokens, const int64_t *d_text_offsets, int64_t num_texts,
+                    int32_t max_n, int64_t min_freq, int64_t max_f_grams, uint64_t seed,
+                    int32_t *d_out_tokens, uint8_t *d_out_lens, int64_t *d_out_counts,
+                    int64_t *out_n, int64_t *out_distinct, void *stream);
 
 /* ---- cache table ------------------------------------------------------------
  * Replaces EmbeddingCache's Dict[int, ndarray] / np.memmap [N, D] fp32 store

@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "lib", "libscone_b200.so")
+# SCONE_B200_LIB: another build of the library (development: the SCONE_TUNE build, A/B against an older build)
+LIB_PATH = os.environ.get("SCONE_B200_LIB") or os.path.join(PKG, "lib", "libscone_b200.so")
 
 QUANT = {"fp16": 0, "int8": 1, "int4": 2, "fp32": 3}
 OUT_BF16, OUT_FP16, OUT_FP32 = 0, 1, 2
@@ -22,7 +23,7 @@ E_INVALID, E_CUDA, E_VOCAB, E_NOMEM = -1, -2, -3, -4
 # every symbol include/scone_b200.h declares (tests check they are all exported)
 SYMBOLS = [
     "scone_version", "scone_last_error", "scone_launch_count", "scone_host_gather_rows",
-    "scone_index_create", "scone_index_destroy", "scone_index_info", "scone_index_lookup", "scone_index_match_all",
+    "scone_index_create", "scone_index_destroy", "scone_index_info", "scone_index_lookup", "scone_index_match_all", "scone_fit_vocab",
     "scone_table_layout", "scone_table_store", "scone_table_store_projected", "scone_table_gather", "scone_table_gather_packed",
     "scone_embed_forward", "scone_embed_forward_additive", "scone_embed_forward_ex", "scone_embed_gather", "scone_embed_forward_sharded", "scone_embed_mean_forward",
     "scone_pipeline_create", "scone_pipeline_submit", "scone_pipeline_follow", "scone_pipeline_wait", "scone_pipeline_destroy",
@@ -31,7 +32,8 @@ SYMBOLS = [
 
 class IndexInfo(C.Structure):
     _fields_ = [("num_fgrams", C.c_int64), ("capacity", C.c_int64), ("bytes", C.c_int64), ("max_n", C.c_int32),
-                ("len_mask", C.c_uint32), ("max_probe", C.c_int32), ("slot_bytes", C.c_int32), ("filter_bytes", C.c_int64)]
+                ("len_mask", C.c_uint32), ("max_probe", C.c_int32), ("slot_bytes", C.c_int32), ("filter_bytes", C.c_int64),
+                ("slot_format", C.c_int32), ("reserved", C.c_int32)]
 
 
 class TableDesc(C.Structure):
@@ -74,6 +76,7 @@ def load() -> C.CDLL:
     L.scone_index_info.argtypes = [vp, C.POINTER(IndexInfo)]
     L.scone_index_lookup.argtypes = [vp, vp, i64, i64, vp, vp, vp]
     L.scone_index_match_all.argtypes = [vp, vp, i64, i64, vp, vp]
+    L.scone_fit_vocab.argtypes = [vp, i64, vp, i64, i32, i64, i64, C.c_uint64, vp, vp, vp, C.POINTER(i64), C.POINTER(i64), vp]
     L.scone_table_layout.argtypes = [i32, i32, i32, i32, C.POINTER(i64), C.POINTER(i32)]
     L.scone_table_store.argtypes = [C.POINTER(TableDesc), vp, vp, i64, i64, vp]
     L.scone_table_store_projected.argtypes = [C.POINTER(TableDesc), vp, vp, i32, vp, i64, i64, vp, vp]

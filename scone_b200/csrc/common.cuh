@@ -74,17 +74,29 @@ struct __align__(16) Slot16 {
 };
 static_assert(sizeof(Slot16) == 16, "compact slot");
 
+// Second compact format, for vocabularies whose tokens do not fit 16 bits (V = 128 000: configs 3-5): 16 bytes = a 28-bit
+// id + FIVE 20-bit tokens (reverse order, 0xFFFFF padded); needs max_n <= 5, tokens < 1 048 575 and fewer than 2^28 - 1
+// f-grams.  Same 64-byte probe step of four slots; the all-ones first word marks an empty slot.
+//   w0 = id | t0[3:0] << 28      w1 = t0[19:4] | t1[15:0] << 16      w2 = t1[19:16] | t2 << 4 | t3[7:0] << 24      w3 = t3[19:8] | t4 << 12
+struct __align__(16) Slot20 {
+    uint32_t w[4];
+};
+static_assert(sizeof(Slot20) == 16, "compact-20 slot");
+constexpr uint32_t kPad20 = 0xFFFFFu, kEmpty20 = 0xFFFFFFFFu, kIdMask20 = 0x0FFFFFFFu;
+
+enum SlotFormat : int32_t { kSlotWide = 0, kSlotCompact16 = 1, kSlotCompact20 = 2 };
+
 struct scone_index_impl {
-    Slot *slots;  // Slot or Slot16 array, `cap` entries
+    Slot *slots;  // Slot, Slot16 or Slot20 array, `cap` entries
     uint64_t cap;
     int64_t n;
     int32_t max_n;
     uint32_t len_mask;
     int32_t max_probe;
-    int32_t compact;
+    int32_t compact;  // SlotFormat
     int device;
     uint32_t *filter;      // pre-filter words (see filter_pass), or NULL
-    uint32_t filter_mask;  // number of words - 1 (a power of two)
+    uint32_t filter_mask;  // number of words (any count: the word is picked by a multiply-high, not a mask)
     int32_t filter_always; // SCONE_INDEX_FILTER=always: consult it for every batch size (testing)
 };
 
@@ -96,7 +108,7 @@ struct IndexView {
     int32_t max_n;
     int32_t compact;
     const uint32_t *filter;  // NULL = probe every candidate
-    uint32_t filter_mask;
+    uint32_t filter_mask;    // number of filter words
 #ifdef SCONE_TUNE
     const uint8_t *hint;  // development only, see match.cuh
 #endif
@@ -204,29 +216,73 @@ __device__ __forceinline__ int32_t probe16(const IndexView &ix, uint64_t h, cons
     return -1;
 }
 
+__device__ __forceinline__ bool pack_key20(const int32_t (&key)[7], uint32_t (&k)[4]) {
+    bool ok = key[5] < 0 && key[6] < 0;  // at most five tokens
+    uint32_t t[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        ok = ok && key[i] < (int32_t)kPad20;
+        t[i] = key[i] < 0 ? kPad20 : (uint32_t)key[i];
+    }
+    k[0] = (t[0] & 0xFu) << 28;  // compared with the top four bits of w0
+    k[1] = (t[0] >> 4) | ((t[1] & 0xFFFFu) << 16);
+    k[2] = (t[1] >> 16) | (t[2] << 4) | ((t[3] & 0xFFu) << 24);
+    k[3] = (t[3] >> 8) | (t[4] << 12);
+    return ok;
+}
+
+__device__ __forceinline__ int32_t probe20(const IndexView &ix, uint64_t h, const int32_t (&key)[7]) {
+    uint32_t k[4];
+    if (!pack_key20(key, k)) return -1;  // a token >= 2^20 - 1 or a sixth token cannot be in a compact-20 vocabulary
+    const Slot20 *slots = reinterpret_cast<const Slot20 *>(ix.slots);
+    uint64_t s = home_slot16(h, ix.cap);
+    for (uint64_t it = 0; it < ix.cap; it += 4) {
+        int32_t a[8], b[8];
+        load_slot(reinterpret_cast<const Slot *>(slots + s), a);      // slots s, s+1
+        load_slot(reinterpret_cast<const Slot *>(slots + s + 2), b);  // slots s+2, s+3
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int32_t *w = (q < 2 ? a : b) + 4 * (q & 1);
+            if ((uint32_t)w[0] == kEmpty20) return -1;
+            if (((uint32_t)w[0] & ~kIdMask20) == k[0] && (uint32_t)w[1] == k[1] && (uint32_t)w[2] == k[2] && (uint32_t)w[3] == k[3])
+                return (int32_t)((uint32_t)w[0] & kIdMask20);
+        }
+        s += 4;
+        if (s == ix.cap) s = 0;
+    }
+    return -1;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Pre-filter: 16 bits of a blocked Bloom filter per f-gram (two bits of one 32-bit word per key, ~1.5 % false
 // positives, no false negatives).  For vocabularies of a few million f-grams it stays resident in L2, and most candidate
 // n-grams of a position are NOT in the vocabulary: answering those from L2 instead of with a random 64-byte DRAM read of
 // a slot takes two thirds of the probe traffic (and DRAM row activations) away from the row gather they compete with.
-// The word index uses the low hash bits, the bit positions bits 32-41; the home slot comes from the top bits.
+// The word index is a multiply-high of the low 32 hash bits with the word count (any count, so the filter is exactly as
+// large as its bits-per-key budget asks), the bit positions come from bits 32-41; the home slot from the top bits.
+// Vocabularies of up to 12 M f-grams get 16 bits per key, up to 48 M f-grams 8 bits per key (~6 % false positives:
+// a 10 M-f-gram filter is 20 MB and still lives in the 126 MB L2 next to the streamed rows), larger ones none.
 // ---------------------------------------------------------------------------------------------
 __host__ __device__ __forceinline__ uint32_t filter_bits(uint64_t h) {
     return (1u << (uint32_t)((h >> 32) & 31u)) | (1u << (uint32_t)((h >> 37) & 31u));
+}
+
+__host__ __device__ __forceinline__ uint32_t filter_word(uint64_t h, uint32_t words) {
+    return (uint32_t)(((uint64_t)(uint32_t)h * (uint64_t)words) >> 32);
 }
 
 __device__ __forceinline__ bool filter_pass(const IndexView &ix, uint64_t h) {
     if (!ix.filter) return true;
     uint32_t w;
     // (L2 default priority is enough: everything streamed is evict-first; the .L2::evict_last form exists for 256-bit loads only)
-    asm volatile("ld.global.nc.L1::evict_last.b32 %0, [%1];" : "=r"(w) : "l"(ix.filter + ((uint32_t)h & ix.filter_mask)));
+    asm volatile("ld.global.nc.L1::evict_last.b32 %0, [%1];" : "=r"(w) : "l"(ix.filter + filter_word(h, ix.filter_mask)));
     const uint32_t b = filter_bits(h);
     return (w & b) == b;
 }
 
 __device__ __forceinline__ int32_t probe_any(const IndexView &ix, uint64_t h, const int32_t (&key)[7]) {
     if (!filter_pass(ix, h)) return -1;
-    return ix.compact ? probe16(ix, h, key) : probe(ix, h, key);
+    return ix.compact == kSlotCompact16 ? probe16(ix, h, key) : ix.compact == kSlotCompact20 ? probe20(ix, h, key) : probe(ix, h, key);
 }
 
 // ---------------------------------------------------------------------------------------------

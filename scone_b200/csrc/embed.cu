@@ -46,10 +46,12 @@ static int dispatch(int P, EmbedParams &p, int quant, int out_dtype, cudaStream_
     if (const char *e = getenv("SCONE_STAGGER_CTA_NS")) p.stagger_cta_ns = atoi(e);
 #endif
     if (p.additive && P < 4) P = 4;  // see launch_p
-    // SCONE_EMBED_PIPE=0 selects embed_bulk_kernel (one ring, the matcher stages its own tile) instead of the three-role
-    // pipeline of embed_pipe.cuh; read per call so that the tests can run both.
+    // Two kernels (measured, profiles/tune_r02.md): the plain path runs fastest on embed_bulk_kernel (one ring, the matcher
+    // stages its own tile: fewest hand-offs); with extra rows per position (fused position add, additive combine) the
+    // three-role pipeline of embed_pipe.cuh keeps full-size tiles and wins.  SCONE_EMBED_PIPE=0 / 1 forces one of them
+    // (read per call so that the tests can run both everywhere).
     const char *pe = getenv("SCONE_EMBED_PIPE");
-    if (!pe || pe[0] != '0') p.flags |= kEmbedPipe;
+    if (pe ? pe[0] != '0' : (p.pos != nullptr || p.additive)) p.flags |= kEmbedPipe;
     if (p.flags & kEmbedPipe) {
         // full-size tiles on any shape before smaller tiles: the pipeline's matchers do not depend on the row ring
         const int pn[] = {kNarrow6, kMid, kWide, kSmall}, pw[] = {kWide, kSmall};

@@ -678,10 +678,11 @@ static int launch_bulk(EmbedParams &p, const BulkLayout &lay, cudaStream_t strea
     return launch_pdl(kern, blocks, 32 * (NM + NG), (size_t)lay.smem_bytes, stream, p, lay);
 }
 
-template <int QUANT, int OUT, int P, int NM, int NG, int MINB, bool ADD>
+template <int QUANT, int OUT, int P, int NM, int NL, int NG, int MINB, bool ADD>
 static int launch_pipe(EmbedParams &p, const PipeLayout &lay, cudaStream_t stream) {
     constexpr int G = 32 / P;
-    auto kern = embed_pipe_kernel<QUANT, OUT, P, NM, NG, MINB, ADD>;
+    static_assert(NL <= G, "a loader without a position");
+    auto kern = embed_pipe_kernel<QUANT, OUT, P, NM, NL, NG, MINB, ADD>;
     static int configured[64] = {0};  // per device: the attribute lives in the device's context
     int dev = 0;
     SCONE_CUDA(cudaGetDevice(&dev));
@@ -692,7 +693,7 @@ static int launch_pipe(EmbedParams &p, const PipeLayout &lay, cudaStream_t strea
     p.num_tiles = (p.T + G - 1) / G;
     const int64_t resident = (int64_t)num_sms() * MINB;
     const unsigned blocks = (unsigned)(p.num_tiles < resident ? p.num_tiles : resident);
-    return launch_pdl(kern, blocks, 32 * (NM + 1 + NG), (size_t)lay.smem_bytes, stream, p, lay);
+    return launch_pdl(kern, blocks, 32 * (NM + NL + NG), (size_t)lay.smem_bytes, stream, p, lay);
 }
 
 // Kernel selection (measured on B200, profiles/tune_r01.md).  Rows that fit a shared-memory ring go through the
@@ -740,6 +741,18 @@ static int launch(EmbedParams &p, cudaStream_t stream, int shape) {
         SCONE_B(3, 12, 1) SCONE_B(6, 12, 1) SCONE_B(6, 4, 3) SCONE_B(4, 4, 3) SCONE_B(2, 6, 3) SCONE_B(2, 12, 1)
 #undef SCONE_B
         if (v.kind == 0) return launch_ldg<QUANT, OUT, P, 4, 2, 6, 4>(p, stream);
+        // kind 2: the three-role pipeline with NM matchers (+ 1 loader) + NG gather warps
+        PipeLayout pv;
+        // (the U field of the variant string is the number of loader warps)
+#define SCONE_PV(NMM, NLL, NGG, MM)                                                                                                    \
+    if (v.kind == 2 && v.nm == NMM && v.u == NLL && v.ng == NGG && v.minb == MM && pipe_layout(p, G, NMM, v.smem_kb * 1024, pv)) \
+        return launch_pipe<QUANT, OUT, P, NMM, NLL, NGG, MM, ADD>(p, pv, stream);
+        if constexpr (P == 4) {
+            SCONE_PV(5, 1, 4, 3) SCONE_PV(6, 1, 4, 3) SCONE_PV(5, 2, 4, 3) SCONE_PV(4, 2, 4, 3) SCONE_PV(4, 2, 8, 2) SCONE_PV(4, 4, 8, 2)
+            SCONE_PV(6, 2, 8, 2) SCONE_PV(6, 4, 8, 2) SCONE_PV(6, 2, 12, 1) SCONE_PV(6, 4, 12, 1) SCONE_PV(8, 4, 12, 1) SCONE_PV(8, 4, 16, 1)
+            SCONE_PV(8, 8, 16, 1) SCONE_PV(6, 1, 12, 1) SCONE_PV(4, 4, 12, 1) SCONE_PV(8, 2, 8, 2)
+        }
+#undef SCONE_PV
     }
 #endif
     if (p.flags & kEmbedPipe) {
@@ -750,19 +763,19 @@ static int launch(EmbedParams &p, cudaStream_t stream, int shape) {
             case kNarrow4:
                 if (pipe_layout(p, G, 5, 70 * 1024, pl)) {
                     set_stagger<P, 5, 3>(p);
-                    return launch_pipe<QUANT, OUT, P, 5, 4, 3, ADD>(p, pl, stream);
+                    return launch_pipe<QUANT, OUT, P, 5, 1, 4, 3, ADD>(p, pl, stream);
                 }
                 return kNoFit;
             case kMid:
-                if (pipe_layout(p, G, 4, 100 * 1024, pl)) return launch_pipe<QUANT, OUT, P, 4, 8, 2, ADD>(p, pl, stream);
+                if (pipe_layout(p, G, 4, 100 * 1024, pl)) return launch_pipe<QUANT, OUT, P, 4, (G >= 2 ? 2 : 1), 8, 2, ADD>(p, pl, stream);
                 return kNoFit;
             case kWide:
             case kWide3:
             case kWide2:
-                if (pipe_layout(p, G, 6, 200 * 1024, pl)) return launch_pipe<QUANT, OUT, P, 6, 12, 1, ADD>(p, pl, stream);
+                if (pipe_layout(p, G, 6, 200 * 1024, pl)) return launch_pipe<QUANT, OUT, P, 6, (G >= 4 ? 4 : G), 12, 1, ADD>(p, pl, stream);
                 return kNoFit;
             case kSmall:
-                if (pipe_layout(p, G, 2, 70 * 1024, pl)) return launch_pipe<QUANT, OUT, P, 2, 6, 3, ADD>(p, pl, stream);
+                if (pipe_layout(p, G, 2, 70 * 1024, pl)) return launch_pipe<QUANT, OUT, P, 2, 1, 6, 3, ADD>(p, pl, stream);
                 return kNoFit;
             default:
                 return launch_ldg<QUANT, OUT, P, 4, 2, 6, 4>(p, stream);

@@ -12,9 +12,11 @@
 //   * matchers only resolve: they write 9 bytes per position into a metadata ring of 4 x NM tiles and never wait for row
 //     storage, so tiles stay at the full G = 32 / P positions whatever a position's rows weigh, and the probe chains of
 //     many tiles are in flight;
-//   * ONE loader warp walks the CTA's tiles in order, waits for a free row slot and issues the bulk copies (lane g stages
-//     position g: table or fallback row [+ base row of a hit] [+ position row]); a single producer, so the row ring only
-//     needs two slots and no slot-ownership rule;
+//   * NL loader warps walk the CTA's tiles in order, wait for a free row slot and issue the bulk copies (position g of a tile
+//     is staged by loader g % NL: table or fallback row [+ base row of a hit] [+ position row]).  Every loader takes part in
+//     every tile, so the row ring only needs two slots and no slot-ownership rule.  Why several: a cp.async.bulk costs
+//     ~80 ns to issue and the issues of one warp serialise -- with three rows per position ONE loader spent 1.9 us per
+//     tile of 8 positions and capped config 2 + base row + wpe at 104 us (profiles/tune_r02.md);
 //   * gather warps are those of embed_bulk_kernel; the one that owns a tile's first position also writes the tile's
 //     fgram_id / match_len (from the slot header), so matchers and loader never write global memory: with
 //     SCONE_EMBED_INPUTS_STABLE they run under the previous kernel's tail without ever waiting for it.
@@ -37,8 +39,8 @@ __host__ __device__ constexpr int pipe_header_bytes(int G) {
     return ((2 * kMaxRing + 2 * kMaxMetaRing) * 8 + (kMaxRing + kMaxMetaRing) * G * 9 + 127) / 128 * 128;
 }
 
-template <int QUANT, int OUT, int P, int NM, int NG, int MINB, bool ADD>
-__global__ void __launch_bounds__(32 * (NM + 1 + NG), MINB) embed_pipe_kernel(const EmbedParams p, const PipeLayout lay) {
+template <int QUANT, int OUT, int P, int NM, int NL, int NG, int MINB, bool ADD>
+__global__ void __launch_bounds__(32 * (NM + NL + NG), MINB) embed_pipe_kernel(const EmbedParams p, const PipeLayout lay) {
     constexpr int G = 32 / P;
     const int add_off = ADD ? lay.add_off : 0;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -58,12 +60,12 @@ __global__ void __launch_bounds__(32 * (NM + 1 + NG), MINB) embed_pipe_kernel(co
     const int warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
         for (int q = 0; q < R; ++q) {
-            mbar_init(&full_bar[q], 1);
+            mbar_init(&full_bar[q], NL);  // one arrival (+ its bytes) per loader
             mbar_init(&empty_bar[q], NG);
         }
         for (int q = 0; q < MR; ++q) {
             mbar_init(&meta_full[q], 1);
-            mbar_init(&meta_empty[q], 1);
+            mbar_init(&meta_empty[q], NL);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -123,8 +125,9 @@ __global__ void __launch_bounds__(32 * (NM + 1 + NG), MINB) embed_pipe_kernel(co
             }
             if (lane == 0) mbar_arrive(&meta_full[ms]);
         }
-    } else if (warp == NM) {
-        // ===== loader warp: tiles in order; lane g stages position g of the tile =====
+    } else if (warp < NM + NL) {
+        // ===== loader warps: tiles in order; lane g of loader g % NL stages position g of the tile =====
+        const int ld = warp - NM;
         const uint64_t pol = policy_evict_first(), pol_keep = policy_evict_last();
         int64_t itl = 0;
         for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++itl) {
@@ -139,7 +142,7 @@ __global__ void __launch_bounds__(32 * (NM + 1 + NG), MINB) embed_pipe_kernel(co
             __syncwarp();
             if (lane == 0) mbar_arrive(&meta_empty[ms]);  // the entries are in registers: the matcher may reuse the slot
             const int64_t i = tile * G + lane;
-            const bool owner = lane < G && i < p.T;
+            const bool owner = lane < G && (lane % NL) == ld && i < p.T;
             const uint8_t *src = nullptr, *src2 = nullptr, *src3 = nullptr;
             uint32_t bytes = 0;
             if (owner) {
@@ -157,14 +160,16 @@ __global__ void __launch_bounds__(32 * (NM + 1 + NG), MINB) embed_pipe_kernel(co
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xFFFFFFFFu, total, o);
             mbar_wait(&empty_bar[q], (uint32_t)(((itl / R) & 1) ^ 1));
+            if (ld == 0) {  // the slot header is written by one thread, before its arrival
 #pragma unroll
-            for (int g = 0; g < G; ++g) {
-                const int32_t f = __shfl_sync(0xFFFFFFFFu, e.x, g);
-                const int32_t k2 = __shfl_sync(0xFFFFFFFFu, e.y, g);
-                const int32_t l2 = __shfl_sync(0xFFFFFFFFu, len, g);
-                if (lane == 0) {
-                    hdr[q * G + g] = make_int2(f, k2);
-                    hdr_len[q * G + g] = (uint8_t)l2;
+                for (int g = 0; g < G; ++g) {
+                    const int32_t f = __shfl_sync(0xFFFFFFFFu, e.x, g);
+                    const int32_t k2 = __shfl_sync(0xFFFFFFFFu, e.y, g);
+                    const int32_t l2 = __shfl_sync(0xFFFFFFFFu, len, g);
+                    if (lane == 0) {
+                        hdr[q * G + g] = make_int2(f, k2);
+                        hdr_len[q * G + g] = (uint8_t)l2;
+                    }
                 }
             }
             if (lane == 0) mbar_arrive_expect_tx(&full_bar[q], total);
@@ -178,7 +183,7 @@ __global__ void __launch_bounds__(32 * (NM + 1 + NG), MINB) embed_pipe_kernel(co
         // ===== gather warps: every warp waits for and releases every tile, in order =====
         bool flagged = false, waited = !early;
         const uint64_t pol = policy_evict_first();
-        const int w = warp - NM - 1;
+        const int w = warp - NM - NL;
         int64_t itl = 0;
         for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++itl) {
             const int q = (int)(itl % R);

@@ -66,9 +66,22 @@ __global__ void __launch_bounds__(256) index_build_kernel(const int32_t *__restr
     }
     if (bad) return;  // counted by the scan
     h = hash_finish(h, len);
-    if (filter) atomicOr(&filter[(uint32_t)h & filter_mask], filter_bits(h));
+    if (filter) atomicOr(&filter[filter_word(h, filter_mask)], filter_bits(h));
     int probes = 1;
-    if (compact) {
+    if (compact == kSlotCompact20) {
+        Slot20 *s20 = reinterpret_cast<Slot20 *>(slots);
+        uint32_t k20[4];
+        pack_key20(key, k20);  // validity was established by the scan pass (max token, max_n)
+        uint64_t s = home_slot16(h, cap);
+        for (;;) {
+            uint32_t old = atomicCAS(&s20[s].w[0], kEmpty20, (uint32_t)i | k20[0]);
+            if (old == kEmpty20) break;
+            if (++s == cap) s = 0;
+            ++probes;
+        }
+#pragma unroll
+        for (int k = 1; k < 4; ++k) s20[s].w[k] = k20[k];
+    } else if (compact == kSlotCompact16) {
         Slot16 *s16 = reinterpret_cast<Slot16 *>(slots);
         uint64_t s = home_slot16(h, cap);
         for (;;) {
@@ -195,12 +208,25 @@ int scone_index_create(const int32_t *d_tokens, const uint8_t *d_lens, int64_t n
         SCONE_CUDA(cudaMemcpyAsync(&h, d_stats, sizeof h, cudaMemcpyDeviceToHost, stream));
         SCONE_CUDA(cudaStreamSynchronize(stream));
         if (h.bad_len || h.bad_tok) return SCONE_OK;  // reported below
-        const char *fmt = getenv("SCONE_INDEX_FORMAT");  // "wide" / "compact" override the automatic choice (testing)
-        ix->compact = (max_n <= 6 && h.max_tok < 0xFFFF) ? 1 : 0;
-        if (fmt && !strcmp(fmt, "wide")) ix->compact = 0;
-        if (fmt && !strcmp(fmt, "compact") && !(max_n <= 6 && h.max_tok < 0xFFFF)) {
-            set_error("scone_index_create: SCONE_INDEX_FORMAT=compact needs max_n <= 6 and tokens < 65535");
-            return SCONE_E_INVALID;
+        const char *fmt = getenv("SCONE_INDEX_FORMAT");  // "wide" / "compact" / "compact20" override the automatic choice (testing)
+        const bool fits16 = max_n <= 6 && h.max_tok < 0xFFFF;
+        const bool fits20 = max_n <= 5 && h.max_tok < (int)kPad20 && n < (int64_t)kIdMask20;
+        ix->compact = fits16 ? kSlotCompact16 : fits20 ? kSlotCompact20 : kSlotWide;
+        if (fmt && !strcmp(fmt, "wide")) ix->compact = kSlotWide;
+        if (fmt && !strcmp(fmt, "compact")) {
+            if (!fits16) {
+                set_error("scone_index_create: SCONE_INDEX_FORMAT=compact needs max_n <= 6 and tokens < 65535");
+                return SCONE_E_INVALID;
+            }
+            ix->compact = kSlotCompact16;
+        }
+        if (fmt && !strcmp(fmt, "prefer-compact20") && fits20) ix->compact = kSlotCompact20;  // testing: small vocabularies too
+        if (fmt && !strcmp(fmt, "compact20")) {
+            if (!fits20) {
+                set_error("scone_index_create: SCONE_INDEX_FORMAT=compact20 needs max_n <= 5, tokens < 1048575 and n < 2^28 - 1");
+                return SCONE_E_INVALID;
+            }
+            ix->compact = kSlotCompact20;
         }
         // default load factor 0.25 for both formats (measured: compact at 0.5 costs config 1 a microsecond of probe chain)
         const double lf = load_factor > 0.0 ? load_factor : 0.25;
@@ -216,20 +242,21 @@ int scone_index_create(const int32_t *d_tokens, const uint8_t *d_lens, int64_t n
             return e == cudaErrorMemoryAllocation ? SCONE_E_NOMEM : SCONE_E_CUDA;
         }
         SCONE_CUDA(cudaMemsetAsync(ix->slots, 0xFF, bytes, stream));
-        // pre-filter (common.cuh: filter_pass): 16 bits per f-gram, built only while it can stay in L2 (<= 16 MB, i.e.
-        // up to 8 M f-grams); SCONE_INDEX_FILTER=never / always override (testing)
+        // pre-filter (common.cuh: filter_pass): 16 bits per f-gram up to 12 M f-grams (24 MB), 8 bits up to 48 M (48 MB), none
+        // above -- it only pays while it stays in L2; SCONE_INDEX_FILTER=never / always override (testing)
         const char *fenv = getenv("SCONE_INDEX_FILTER");
         const bool f_never = fenv && !strcmp(fenv, "never"), f_always = fenv && !strcmp(fenv, "always");
-        if (n > 0 && !f_never && (f_always || n <= (8ll << 20))) {
-            uint64_t words = 1024;
-            while (words < (uint64_t)(n + 1) / 2) words <<= 1;
+        if (n > 0 && !f_never && (f_always || n <= 48000000ll)) {
+            uint64_t words = (uint64_t)(n <= 12000000ll ? (n + 1) / 2 : (n + 3) / 4);
+            if (words < 1024) words = 1024;
+            words = (words + 31) & ~31ull;
             e = cudaMalloc(&ix->filter, words * sizeof(uint32_t));
             if (e != cudaSuccess) {
                 set_error("scone_index_create: cudaMalloc of %llu filter bytes failed: %s", (unsigned long long)(words * 4), cudaGetErrorString(e));
                 ix->filter = nullptr;
                 return e == cudaErrorMemoryAllocation ? SCONE_E_NOMEM : SCONE_E_CUDA;
             }
-            ix->filter_mask = (uint32_t)(words - 1);
+            ix->filter_mask = (uint32_t)words;
             ix->filter_always = f_always ? 1 : 0;
             SCONE_CUDA(cudaMemsetAsync(ix->filter, 0, words * sizeof(uint32_t), stream));
         }
@@ -286,12 +313,13 @@ int scone_index_info(const scone_index_t *index, scone_index_info_t *info) {
     const scone_index_impl *ix = reinterpret_cast<const scone_index_impl *>(index);
     info->num_fgrams = ix->n;
     info->capacity = (int64_t)ix->cap;
-    info->filter_bytes = ix->filter ? ((int64_t)ix->filter_mask + 1) * 4 : 0;
+    info->filter_bytes = ix->filter ? (int64_t)ix->filter_mask * 4 : 0;
     info->bytes = (int64_t)(ix->cap * (ix->compact ? sizeof(Slot16) : sizeof(Slot))) + info->filter_bytes;
     info->max_n = ix->max_n;
     info->len_mask = ix->len_mask;
     info->max_probe = ix->max_probe;
     info->slot_bytes = (int32_t)(ix->compact ? sizeof(Slot16) : sizeof(Slot));
+    info->slot_format = ix->compact;
     return SCONE_OK;
 }
 

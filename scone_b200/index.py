@@ -30,8 +30,10 @@ class FGramIndex:
     def __init__(self, vocab_tokens: torch.Tensor, vocab_lens: torch.Tensor, load_factor: float = 0.0):
         """vocab_tokens int32 [N, max_n] (reading order, padded with -1), vocab_lens uint8 [N]; id = row.
         load_factor 0 = the library default (0.25).  Compact 16-byte slots are used automatically when all tokens are
-        < 65535 and max_n <= 6, 32-byte slots otherwise (``slot_bytes``).  Vocabularies of up to 8 M f-grams also get a
-        16-bit-per-f-gram Bloom pre-filter (``filter_bytes``) that large batches consult before touching a slot."""
+        < 65535 and max_n <= 6 (six 16-bit tokens) or < 1048575 and max_n <= 5 (five 20-bit tokens: V = 128 000),
+        32-byte slots otherwise (``slot_bytes`` / ``slot_format``).  Vocabularies of up to 48 M f-grams also get a Bloom
+        pre-filter (``filter_bytes``: 16 bits per f-gram up to 12 M, 8 bits above) that large batches consult before
+        touching a slot."""
         _require_cuda(vocab_tokens, "vocab_tokens")
         _require_cuda(vocab_lens, "vocab_lens")
         if vocab_tokens.dtype != torch.int32 or vocab_lens.dtype != torch.uint8:
@@ -52,6 +54,7 @@ class FGramIndex:
         self.capacity, self.bytes = int(info.capacity), int(info.bytes)
         self.len_mask, self.max_probe = int(info.len_mask), int(info.max_probe)
         self.slot_bytes = int(info.slot_bytes)
+        self.slot_format = ("wide32", "compact16", "compact20")[int(info.slot_format)]
         self.filter_bytes = int(info.filter_bytes)     # L2-resident pre-filter (0 = none), included in `bytes`
 
     @property

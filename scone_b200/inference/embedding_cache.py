@@ -188,8 +188,9 @@ class EmbeddingCache:
             if self.tier != "hbm":
                 raise ValueError("projection folding is available for the hbm tier")
             chunk = max(1, (256 << 20) // (4 * width))
+            proj = projection.detach().to(device=self.device, dtype=torch.bfloat16)
             for s in range(0, len(ids), chunk):
-                table.store_projected(embeddings[s:s + chunk], projection, id_t[s:s + chunk])
+                table.store_projected(embeddings[s:s + chunk].to(self.device, non_blocking=True), proj, id_t[s:s + chunk])
             self._present[id_t] = True
             return
         if self.tier == "sharded":

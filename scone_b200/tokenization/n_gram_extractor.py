@@ -135,6 +135,8 @@ class NGramExtractor:
         (sort + run-length) instead of a Python ``Counter``.
         """
         texts = [np.asarray(t, dtype=np.int64).ravel() for t in tokenized_texts]
+        if any(t.size and (t.min() < 0 or t.max() > 0x7FFFFFFF) for t in texts):
+            raise ValueError("token ids must be in [0, 2^31)")       # -1 is the padding value of the flat arrays
         max_n = self.max_n
         stride = max([len(t) for t in texts] + [1])
         uniq_rows, uniq_cnt, uniq_first = [], [], []
@@ -186,55 +188,48 @@ class NGramExtractor:
                    device: Optional[torch.device] = None) -> "NGramExtractor":
         """``fit`` on the GPU: same vocabulary and ids as :meth:`fit` / the reference.
 
-        The corpus is flattened once; for each n the valid windows (never across texts) are de-duplicated with a device
-        sort (``torch.unique(dim=0)``), counted, and tagged with their first occurrence in the reference's enumeration
-        order (text, n, start) by a scatter-min; one stable sort by (-count, first seen) ranks all lengths together,
-        then truncate to ``max_f_grams`` and drop counts below ``min_freq`` (reference :91-94, in that order).
+        ``scone_fit_vocab`` (``csrc/fit.cu``): every n-gram occurrence is hashed to 64 bits in the reference's enumeration
+        order (text, n, start), the hashes are radix-sorted (stable: the first member of a run is the n-gram's first
+        occurrence), runs are counted and verified to hold a single n-gram, then ranked by (count descending, first
+        occurrence ascending); truncate to ``max_f_grams``, then drop counts below ``min_freq`` (reference :91-94, in
+        that order).  No ``[M, n]`` key rows are materialised: 32 bytes of scratch per occurrence.
         """
+        import ctypes as C
+        from .. import _lib
+        from ..index import _stream_ptr
         dev = torch.device(device) if device is not None else (torch.device(self.device) if self.device else _default_device())
+        if dev.type != "cuda":
+            raise ValueError("scone_b200 has no CPU path: device must be CUDA")
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
         texts = [np.asarray(t, dtype=np.int64).ravel() for t in tokenized_texts]
         max_n = self.max_n
         lens_np = np.array([len(t) for t in texts], dtype=np.int64)
         M = int(lens_np.sum())
-        rows_l, cnt_l, first_l = [], [], []
-        if M:
-            flat = torch.from_numpy(np.concatenate(texts)).to(dev)
-            if bool((flat < 0).any()) or bool((flat > 0x7FFFFFFF).any()):
+        self._tokens = np.zeros((0, max_n), dtype=np.int32)
+        self._lens = np.zeros((0,), dtype=np.uint8)
+        if M and self.max_f_grams > 0:
+            flat64 = np.concatenate(texts)
+            if flat64.min() < 0 or flat64.max() > 0x7FFFFFFF:
                 raise ValueError("token ids must be in [0, 2^31)")
-            lens_t = torch.from_numpy(lens_np).to(dev)
-            text_id = torch.repeat_interleave(torch.arange(len(texts), device=dev), lens_t)
-            offs = torch.cumsum(lens_t, 0) - lens_t
-            start = torch.arange(M, device=dev) - offs[text_id]
-            stride = int(max(1, lens_np.max()))
-            big = torch.iinfo(torch.int64).max
-            for n in range(1, max_n + 1):
-                if M < n:
-                    break
-                p = torch.arange(M - n + 1, device=dev)
-                ok = text_id[p] == text_id[p + n - 1]
-                p = p[ok]
-                if p.numel() == 0:
-                    continue
-                keys = torch.stack([flat[p + k] for k in range(n)], dim=1)
-                uniq, inv, cnt = torch.unique(keys, dim=0, return_inverse=True, return_counts=True)
-                seen = (text_id[p] * max_n + (n - 1)) * stride + start[p]
-                first = torch.full((uniq.shape[0],), big, dtype=torch.int64, device=dev).scatter_reduce_(0, inv, seen, "amin")
-                rows = torch.full((uniq.shape[0], max_n), -1, dtype=torch.int64, device=dev)
-                rows[:, :n] = uniq
-                rows_l.append(rows)
-                cnt_l.append(cnt)
-                first_l.append(first)
-        if rows_l:
-            rows, cnt, first = torch.cat(rows_l), torch.cat(cnt_l), torch.cat(first_l)
-            order = torch.argsort(first)
-            order = order[torch.argsort(-cnt[order], stable=True)][: self.max_f_grams]
-            order = order[cnt[order] >= self.min_freq]
-            rows = rows[order]
-            self._tokens = rows.to(torch.int32).cpu().numpy()
-            self._lens = (rows >= 0).sum(dim=1).to(torch.uint8).cpu().numpy()
-        else:
-            self._tokens = np.zeros((0, max_n), dtype=np.int32)
-            self._lens = np.zeros((0,), dtype=np.uint8)
+            flat = torch.from_numpy(flat64.astype(np.int32)).to(dev)
+            offs = torch.from_numpy(np.concatenate([[0], np.cumsum(lens_np)]).astype(np.int64)).to(dev)
+            cap = int(min(self.max_f_grams, M * max_n))
+            out_tok = torch.empty((cap, max_n), dtype=torch.int32, device=dev)
+            out_len = torch.empty((cap,), dtype=torch.uint8, device=dev)
+            n_out, distinct = C.c_int64(0), C.c_int64(0)
+            L = _lib.load()
+            with torch.cuda.device(dev):
+                for attempt in range(4):               # a 64-bit hash shared by two n-grams is detected, never trusted: new seed
+                    rc = L.scone_fit_vocab(flat.data_ptr(), M, offs.data_ptr(), len(texts), max_n, int(self.min_freq), cap,
+                                           C.c_uint64(0x5C0E + attempt), out_tok.data_ptr(), out_len.data_ptr(), None,
+                                           C.byref(n_out), C.byref(distinct), _stream_ptr(dev))
+                    if rc != _lib.E_VOCAB:
+                        break
+                _lib.check(rc)
+            k = int(n_out.value)
+            self._tokens = out_tok[:k].cpu().numpy()
+            self._lens = out_len[:k].cpu().numpy()
         self._maps = None
         self._drop_index()
         if verbose:

@@ -18,15 +18,21 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
-@pytest.fixture(autouse=True, params=["auto", "wide"])
+@pytest.fixture(autouse=True, params=["auto", "wide", "c20"])
 def index_format(request, monkeypatch):
     """Every test runs twice: with the library defaults (compact 16-byte slots whenever the tokens allow; the Bloom
-    pre-filter consulted by large batches only; the three-role pipeline kernel of embed_pipe.cuh), and with the 32-byte slot
-    format forced, the pre-filter consulted for every batch size and the single-ring kernel (embed_bulk_kernel) selected."""
+    pre-filter consulted by large batches only; kernel chosen per mode), with the 32-byte slot format forced, the pre-filter
+    consulted for every batch size and the single-ring kernel (embed_bulk_kernel) for every mode, and with the second compact
+    slot format preferred and the three-role pipeline kernel (embed_pipe.cuh) for every mode."""
     if request.param == "wide":
         monkeypatch.setenv("SCONE_INDEX_FORMAT", "wide")
         monkeypatch.setenv("SCONE_INDEX_FILTER", "always")
         monkeypatch.setenv("SCONE_EMBED_PIPE", "0")
+    elif request.param == "c20":
+        # the second compact slot format (five 20-bit tokens; what V = 128 000 vocabularies get) wherever it fits (max_n <= 5)
+        monkeypatch.setenv("SCONE_INDEX_FORMAT", "prefer-compact20")
+        monkeypatch.setenv("SCONE_INDEX_FILTER", "always")
+        monkeypatch.setenv("SCONE_EMBED_PIPE", "1")             # the pipeline kernel for every mode, the plain path included
     else:
         monkeypatch.delenv("SCONE_INDEX_FORMAT", raising=False)
         monkeypatch.delenv("SCONE_INDEX_FILTER", raising=False)
@@ -611,6 +617,14 @@ def test_fit_device_matches_reference_fit():
         a = sb.NGramExtractor(max_n, min_freq, cap).fit_device(corpus, verbose=False)
         want = po.fit(corpus, max_n, min_freq, cap)
         assert [a.id_to_f_gram[i] for i in range(len(a))] == want
+    # a corpus of 2 M tokens: identical to the host fit (which is pinned to the reference), many ties, truncation at work
+    big = [rng.integers(0, 3000, size=int(rng.integers(10, 4000))).tolist() for _ in range(1000)]
+    h = sb.NGramExtractor(4, 3, 200_000).fit(big, verbose=False)
+    d = sb.NGramExtractor(4, 3, 200_000).fit_device(big, verbose=False)
+    assert np.array_equal(h.vocab_arrays()[0], d.vocab_arrays()[0]) and np.array_equal(h.vocab_arrays()[1], d.vocab_arrays()[1])
+    assert len(d) > 50_000
+    with pytest.raises(ValueError):
+        sb.NGramExtractor(2, 1, 10).fit_device([[3, -1, 3]], verbose=False)
 
 
 def test_binary_format_and_reference_memmap_import(tmp_path):
@@ -881,9 +895,9 @@ def test_every_fused_entry_validates_its_buffers():
 
 
 def test_config3_full_size_against_c_oracle(index_format):
-    """BASELINE config 3 at its named size on the device: 10 M f-grams (V = 128 000: the 32-byte slot format, 1.28 GB of
-    slots addressed past 2^31 bytes, no pre-filter above 8 M f-grams), D = 4096 INT4 g128 rows (21 GB table), 256 x 2048
-    positions.  f-gram ids and match lengths of the WHOLE batch and the embeddings of 8 batch rows against the C oracle
+    """BASELINE config 3 at its named size on the device: 10 M f-grams (V = 128 000: compact 20-bit-token slots, a 20 MB
+    pre-filter; and once more with 32-byte slots -- 1.28 GB addressed past 2^31 bytes -- and no filter), D = 4096 INT4 g128
+    rows (21 GB table), 256 x 2048 positions.  f-gram ids and match lengths of the WHOLE batch and the embeddings of 8 batch rows against the C oracle
     (built over the whole vocabulary; the table is one quantised 65 536-row block tiled, which is how bench.py fills it),
     plus the oracle-independent properties of the whole output."""
     if index_format != "auto":
@@ -892,7 +906,7 @@ def test_config3_full_size_against_c_oracle(index_format):
     N, D, V, max_n, B, L, BLK = 10_000_000, 4096, 128_000, 5, 256, 2048, 65536
     toks, lens, longest = S.make_vocab_device(N, max_n, V, seed=0, device=DEV, return_longest=True)
     ix = sb.FGramIndex(toks, lens)
-    assert ix.slot_bytes == 32 and ix.filter_bytes == 0 and ix.bytes > (1 << 30)
+    assert ix.slot_format == "compact20" and ix.slot_bytes == 16 and ix.filter_bytes == 20_000_000 and ix.bytes > (600 << 20)
     blk = sb.CacheTable(BLK, D, "int4")
     S.fill_table_device(blk, seed=2)
     t = sb.CacheTable(N, D, "int4")
@@ -931,6 +945,17 @@ def test_config3_full_size_against_c_oracle(index_format):
     assert torch.equal(win, toks[fid.flatten()[i].long()])
     out2, fid2, _ = sb.embed_forward(ix, t, base, q, inputs_stable=True)
     assert torch.equal(out2, out) and torch.equal(fid2, fid)                          # deterministic
+    # (4) the same vocabulary in 32-byte slots without a filter (slot addresses beyond 2^31 bytes), and through the single-ring kernel
+    import os
+    os.environ.update(SCONE_INDEX_FORMAT="wide", SCONE_INDEX_FILTER="never", SCONE_EMBED_PIPE="0")
+    try:
+        ixw = sb.FGramIndex(toks, lens)
+        assert ixw.slot_bytes == 32 and ixw.filter_bytes == 0 and ixw.bytes > (1 << 30)
+        out3, fid3, ml3 = sb.embed_forward(ixw, t, base, q)
+        assert torch.equal(fid3, fid) and torch.equal(ml3, ml) and torch.equal(out3, out)
+    finally:
+        for k_ in ("SCONE_INDEX_FORMAT", "SCONE_INDEX_FILTER", "SCONE_EMBED_PIPE"):
+            os.environ.pop(k_, None)
 
 
 @pytest.mark.skipif(torch.cuda.is_available() and torch.cuda.device_count() < 2, reason="needs 2 GPUs")

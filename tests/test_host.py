@@ -23,7 +23,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     for name in declared:
         assert getattr(L, name) is not None
     assert L.scone_version() == _lib.ABI_VERSION == int(re.search(r"#define SCONE_B200_VERSION (\d+)", header).group(1))
-    assert ctypes.sizeof(_lib.TableDesc) == 40 and ctypes.sizeof(_lib.IndexInfo) == 48 and ctypes.sizeof(_lib.EmbedOpts) == 16
+    assert ctypes.sizeof(_lib.TableDesc) == 40 and ctypes.sizeof(_lib.IndexInfo) == 56 and ctypes.sizeof(_lib.EmbedOpts) == 16
 
 
 def test_table_layout_matches_oracle_packing():
@@ -66,6 +66,8 @@ def test_host_fit_matches_reference_fixtures():
     assert np.array_equal(ex.vocab_arrays()[0], k["vocab_tokens"])
     ex = NGramExtractor(2, 2, 3).fit([[7, 8, 7, 8, 9]], verbose=False)
     assert ex.f_gram_to_id == {(7,): 0, (8,): 1, (7, 8): 2}
+    with pytest.raises(ValueError):
+        NGramExtractor(2, 1, 10).fit([[3, -1, 3, -1]], verbose=False)          # -1 is the arrays' padding value: refused, not miscounted
     # fuzz against the oracle's restatement of fit
     rng = np.random.default_rng(8)
     for _ in range(25):
@@ -148,12 +150,11 @@ def test_prefilter_parameters_give_the_documented_false_positive_rate(n_keys):
     n = 4
     keys = rng.integers(0, 50_257, size=(n_keys, n), dtype=np.int64)
     probes = rng.integers(0, 50_257, size=(200_000, n), dtype=np.int64)
-    words = 1024
-    while words < (n_keys + 1) // 2:                      # scone_index_create
-        words <<= 1
-    assert 16 * n_keys <= 32 * words < 64 * n_keys + 32 * 1024
+    words = max(1024, (n_keys + 1) // 2)                  # scone_index_create: 16 bits per key up to 12 M f-grams
+    words = (words + 31) & ~31
+    assert 16 * n_keys <= 32 * words < 16 * n_keys + 32 * 1024 + 1024
     def word_and_bits(h):
-        w = (h & u(0xFFFFFFFF)) & u(words - 1)
+        w = ((h & u(0xFFFFFFFF)) * u(words)) >> u(32)     # common.cuh: filter_word
         b = (u(1) << ((h >> u(32)) & u(31))) | (u(1) << ((h >> u(37)) & u(31)))
         return w.astype(np.int64), b.astype(np.uint32)
     filt = np.zeros(words, dtype=np.uint32)
