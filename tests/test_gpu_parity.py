@@ -118,13 +118,23 @@ def test_index_build_audit():
     e = _index(np.zeros((0, 3), np.int32), np.zeros((0,), np.uint8))
     assert e.lookup(torch.tensor([[1, 2, 3]], device=DEV))[0].tolist() == [[-1, -1, -1]]
     assert e.len_mask == 0
-    # slot format: compact when every token < 65535 and max_n <= 6, unless forced wide
+    # slot format: compact (six 16-bit tokens) when every token < 65535 and max_n <= 6; compact (five 20-bit tokens) when every
+    # token < 1048575 and max_n <= 5; 32-byte slots otherwise or when forced
     import os
+    fmt = os.environ.get("SCONE_INDEX_FORMAT")
     small = _index(np.array([[1, 2]], np.int32), np.array([2], np.uint8))
     big = _index(np.array([[1, 70000]], np.int32), np.array([2], np.uint8))
-    assert small.slot_bytes == (32 if os.environ.get("SCONE_INDEX_FORMAT") == "wide" else 16) and big.slot_bytes == 32
+    huge = _index(np.array([[1, 1048575]], np.int32), np.array([2], np.uint8))
+    long6 = _index(np.array([[1, 70000, 3, 4, 5, 6]], np.int32), np.array([6], np.uint8))
+    assert small.slot_format == {"wide": "wide32", "prefer-compact20": "compact20"}.get(fmt, "compact16")
+    assert big.slot_format == ("wide32" if fmt == "wide" else "compact20") and big.slot_bytes == (32 if fmt == "wide" else 16)
+    assert huge.slot_format == "wide32" and long6.slot_format == "wide32" and huge.slot_bytes == 32
     fid, _ = big.lookup(torch.tensor([[1, 70000, 65535, 1, 70000]], device=DEV))
     assert fid.tolist() == [[-1, 0, -1, -1, 0]]
+    fid, _ = big.lookup(torch.tensor([[1, 70000 + (1 << 20), 1, 1048575, 1, 70000]], device=DEV))   # 20-bit aliases must not match
+    assert fid.tolist() == [[-1, -1, -1, -1, -1, 0]]
+    fid, _ = huge.lookup(torch.tensor([[1, 1048575, 1, 1048574]], device=DEV))
+    assert fid.tolist() == [[-1, 0, -1, -1]]
     fid, _ = small.lookup(torch.tensor([[1, 2, 65535, 65536 + 1, 2, 1, 2]], device=DEV))     # 65537 must not alias token 1
     assert fid.tolist() == [[-1, 0, -1, -1, -1, -1, 0]]
 
