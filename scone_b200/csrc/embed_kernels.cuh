@@ -761,9 +761,9 @@ static int launch(EmbedParams &p, cudaStream_t stream, int shape) {
         switch (shape) {
             case kNarrow6:
             case kNarrow4:
-                if (pipe_layout(p, G, 5, 70 * 1024, pl)) {
-                    set_stagger<P, 5, 3>(p);
-                    return launch_pipe<QUANT, OUT, P, 5, 1, 4, 3, ADD>(p, pl, stream);
+                if (pipe_layout(p, G, 6, 70 * 1024, pl)) {
+                    set_stagger<P, 6, 3>(p);
+                    return launch_pipe<QUANT, OUT, P, 6, 1, 4, 3, ADD>(p, pl, stream);
                 }
                 return kNoFit;
             case kMid:
