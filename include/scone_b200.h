@@ -266,6 +266,13 @@ int scone_embed_forward_sharded(const scone_index_t *index, const scone_table_de
                                 void *d_out, int32_t out_dtype,
                                 int32_t *d_out_id, uint8_t *d_out_len, uint32_t *d_status, void *stream);
 
+/* Offloaded tier: host memory for a table the GPU reads in place (the role of the reference's np.memmap backing store,
+ * scone/inference/embedding_cache.py:76-91).  An anonymous mapping on transparent huge pages, first-touched by `nthreads`
+ * host threads, registered with the driver as mapped + portable pinned memory.  *out_device is the pointer to put into
+ * scone_table_desc_t.d_rows.  Release with scone_host_free(host pointer, same byte count). */
+int scone_host_alloc(int64_t bytes, int32_t nthreads, void **out_host, void **out_device);
+int scone_host_free(void *host, int64_t bytes);
+
 /* Offloaded tier, STAGED variant (host code, no GPU work): copy rows h_row_ids[0..k) of a host-resident table into a
  * contiguous pinned staging buffer with `nthreads` host threads, ready for one cudaMemcpyAsync.  The zero-copy
  * variant needs nothing special: point scone_table_desc_t.d_rows at the pinned (UVA-mapped) table.

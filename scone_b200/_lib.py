@@ -22,7 +22,7 @@ E_INVALID, E_CUDA, E_VOCAB, E_NOMEM = -1, -2, -3, -4
 
 # every symbol include/scone_b200.h declares (tests check they are all exported)
 SYMBOLS = [
-    "scone_version", "scone_last_error", "scone_launch_count", "scone_host_gather_rows",
+    "scone_version", "scone_last_error", "scone_launch_count", "scone_host_gather_rows", "scone_host_alloc", "scone_host_free",
     "scone_index_create", "scone_index_destroy", "scone_index_info", "scone_index_lookup", "scone_index_match_all", "scone_fit_vocab",
     "scone_table_layout", "scone_table_store", "scone_table_store_projected", "scone_table_gather", "scone_table_gather_packed",
     "scone_embed_forward", "scone_embed_forward_additive", "scone_embed_forward_ex", "scone_embed_gather", "scone_embed_forward_sharded", "scone_embed_mean_forward",
@@ -83,6 +83,8 @@ def load() -> C.CDLL:
     L.scone_table_gather.argtypes = [C.POINTER(TableDesc), vp, i64, vp, i32, vp, vp]
     L.scone_table_gather_packed.argtypes = [C.POINTER(TableDesc), vp, i64, vp, vp, vp]
     L.scone_host_gather_rows.argtypes = [vp, i64, i64, vp, i64, vp, i32]
+    L.scone_host_alloc.argtypes = [i64, i32, C.POINTER(vp), C.POINTER(vp)]
+    L.scone_host_free.argtypes = [vp, i64]
     L.scone_embed_forward.argtypes = [vp, C.POINTER(TableDesc), vp, i64, vp, vp, i64, i64, vp, i32, vp, vp, vp, vp]
     L.scone_embed_forward_additive.argtypes = L.scone_embed_forward.argtypes
     L.scone_embed_forward_ex.argtypes = [vp, C.POINTER(TableDesc), vp, i64, vp, vp, i64, i64, vp, i32, vp, vp, vp, C.POINTER(EmbedOpts), vp]

@@ -22,6 +22,13 @@ def table_layout(quant: str, dim: int, group: int = 128, align: int = 32) -> Tup
     return int(rs.value), int(so.value)
 
 
+def _free_host(ptr: int, nbytes: int) -> None:
+    try:
+        _lib.load().scone_host_free(ptr, nbytes)
+    except Exception:
+        pass
+
+
 class CacheTable:
     """N rows of D elements stored as FP32 (unquantised, the reference's own storage) / FP16 / INT8 (per-row scale) /
     INT4 (per-group fp16 scales).
@@ -47,12 +54,14 @@ class CacheTable:
         elif tier == "hbm":
             self.storage = torch.zeros((self.num_rows, self.row_stride), dtype=torch.uint8, device=self.device)
         elif tier == "host":
-            self.storage = torch.zeros((self.num_rows, self.row_stride), dtype=torch.uint8, pin_memory=True)
+            self.storage = self._alloc_host(self.num_rows * self.row_stride).view(self.num_rows, self.row_stride)
         else:
             raise ValueError("tier must be 'hbm' or 'host'")
         if tier == "hbm":
             _require_cuda(self.storage, "storage")
             self._dev_ptr = self.storage.data_ptr()
+        elif self._host_dev_ptr is not None:
+            self._dev_ptr = self._host_dev_ptr
         else:
             if not self.storage.is_pinned():
                 raise ValueError("host-tier storage must be pinned")
@@ -60,6 +69,26 @@ class CacheTable:
             self._dev_ptr = self.storage.data_ptr()
         self.desc = _lib.TableDesc(self._dev_ptr, self.row_stride, self.num_rows, _lib.QUANT[quant], self.dim, self.group,
                                    self.scale_offset)
+
+    _host_dev_ptr = None
+
+    def _alloc_host(self, nbytes: int) -> torch.Tensor:
+        """Zero-filled host memory the GPU reads in place: ``scone_host_alloc`` (huge pages, parallel first touch, registered
+        as mapped pinned memory).  ``SCONE_HOST_ALLOC=torch`` falls back to a ``pin_memory=True`` torch allocation."""
+        import os
+        import weakref
+        nbytes = max(int(nbytes), 1)
+        if os.environ.get("SCONE_HOST_ALLOC") == "torch":
+            return torch.zeros((nbytes,), dtype=torch.uint8, pin_memory=True)
+        host, dev = C.c_void_p(), C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().scone_host_alloc(nbytes, min(32, os.cpu_count() or 1), C.byref(host), C.byref(dev)))
+        buf = (C.c_uint8 * nbytes).from_address(host.value)
+        t = torch.frombuffer(buf, dtype=torch.uint8)
+        self._host_dev_ptr = dev.value
+        self._host_region = (host.value, nbytes)
+        weakref.finalize(self, _free_host, host.value, nbytes)
+        return t
 
     @property
     def bytes(self) -> int:

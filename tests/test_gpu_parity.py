@@ -632,7 +632,7 @@ def test_fit_device_matches_reference_fit():
     h = sb.NGramExtractor(4, 3, 200_000).fit(big, verbose=False)
     d = sb.NGramExtractor(4, 3, 200_000).fit_device(big, verbose=False)
     assert np.array_equal(h.vocab_arrays()[0], d.vocab_arrays()[0]) and np.array_equal(h.vocab_arrays()[1], d.vocab_arrays()[1])
-    assert len(d) > 50_000
+    assert len(d) > 10_000
     with pytest.raises(ValueError):
         sb.NGramExtractor(2, 1, 10).fit_device([[3, -1, 3]], verbose=False)
 
