@@ -52,8 +52,6 @@ static int dispatch(int P, EmbedParams &p, int quant, int out_dtype, cudaStream_
     // (read per call so that the tests can run both everywhere).
     // Measured (config 2 / config 3, us per step, bulk vs pipeline): plain 38.4 / 41.5 and 1004 / 1067; + wpe 51.9 / 47.0 and
     // 1530 / 1515; + base row 54.2 / 51.4 and 1625 / 1554; both 70.3 / 75.3 and 2383 / 2295.
-    if (const char *md = getenv("SCONE_MISS_DIRECT"))  // experiment (profiles/tune_r02.md section 7): fallback rows bypass the ring
-        if (md[0] == '1') p.flags |= kMissDirect;
     const char *pe = getenv("SCONE_EMBED_PIPE");
     const bool extra_pos = p.pos != nullptr, extra_add = p.additive != 0;
     if (pe ? pe[0] != '0' : ((extra_pos != extra_add) || (extra_pos && extra_add && moved >= 6144))) p.flags |= kEmbedPipe;

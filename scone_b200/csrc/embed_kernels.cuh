@@ -77,7 +77,6 @@ __device__ __forceinline__ const uint8_t *row_ptr(const EmbedParams &p, int32_t 
 
 constexpr int kRing = 16;  // tiles the matchers may run ahead of the gather warps
 constexpr uint32_t kEmbedPipe = 1u << 31;  // EmbedParams::flags, internal: use embed_pipe_kernel instead of embed_bulk_kernel
-constexpr uint32_t kMissDirect = 1u << 30;  // internal: fallback rows are not staged in the ring (see BulkLayout::miss_direct)
 
 // programmatic dependent launch: block until the grid this one was launched behind has completed and its writes are visible
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
@@ -331,8 +330,6 @@ struct BulkLayout {
     int pos_off;     // offset of the position-embedding row inside a position's slot, 0 = no position add
     int add_off;     // offset of the base row staged next to a HIT's table row (additive combine), 0 = replace mode
     int smem_bytes;  // dynamic shared memory per CTA
-    int miss_direct;  // 1: a slot only holds a table row (row_stride < 2 D: INT8 / INT4); the fallback row of a miss is copied by
-                      // its gather warp straight from global memory.  The ring then holds 2 D / row_stride times more tiles.
 };
 
 // 8 elements (chunk c) of a table row staged in shared memory -> fp32
@@ -509,7 +506,7 @@ __global__ void __launch_bounds__(32 * (NM + NG), MINB) embed_bulk_kernel(const 
                 if (fid >= 0) {
                     src = row_ptr(p, fid);
                     bytes = (uint32_t)p.row_stride;
-                } else if (tok >= 0 && !lay.miss_direct) {
+                } else if (tok >= 0) {
                     src = p.base + (int64_t)tok * p.D * 2;
                     bytes = (uint32_t)p.D * 2u;
                 }
@@ -570,11 +567,8 @@ __global__ void __launch_bounds__(32 * (NM + NG), MINB) embed_bulk_kernel(const 
                 if (t < p.T) {
                     const uint8_t *slot = rows_smem + (size_t)(q * G + j) * lay.slot_bytes;
                     const uint8_t *arow = (add_off && e.x >= 0 && e.y >= 0) ? slot + add_off : nullptr;
-                    if (lay.miss_direct && e.x < 0 && e.y >= 0)
-                        stream_miss<4>(p, e.y, p.out + t * p.D * 2, lane, pol);  // the fallback row was not staged: global -> global
-                    else
-                        stream_from_smem<QUANT, OUT>(p, slot, arow, lay.pos_off ? slot + lay.pos_off : nullptr, e.x, e.y, p.out + t * p.D * 2,
-                                                     lane, pol);
+                    stream_from_smem<QUANT, OUT>(p, slot, arow, lay.pos_off ? slot + lay.pos_off : nullptr, e.x, e.y, p.out + t * p.D * 2, lane,
+                                                 pol);
                     flagged |= e.y < 0 && (e.x < 0 || add_off);
                 }
             }
@@ -647,11 +641,6 @@ static int launch_ldg(EmbedParams &p, cudaStream_t stream) {
 // parity wait on slot t % ring is never more than one phase ahead.
 static bool bulk_layout(const EmbedParams &p, int G, int nm, int budget_bytes, BulkLayout &lay) {
     int64_t slot = p.row_stride > 2ll * p.D ? p.row_stride : 2ll * p.D;
-    lay.miss_direct = 0;
-    if ((p.flags & kMissDirect) && !p.additive && !p.pos && p.row_stride < 2ll * p.D) {
-        slot = p.row_stride;  // only table rows are staged
-        lay.miss_direct = 1;
-    }
     slot = (slot + 127) / 128 * 128;
     lay.pos_off = lay.add_off = 0;
     if (p.additive) {  // room for a hit's base row behind the table row
