@@ -452,6 +452,34 @@ def run_ours(args, w, rank, local_rank, world, name):
     if rank != 0:
         return None
 
+    # ---- in-run parity: two rows of batch 0 through the drop-in class against the oracle ---------------------------------
+    parity = None
+    if not args.no_parity:
+        try:
+            from oracle import py_oracle as po
+            from oracle.c_oracle import COracleIndex
+            t0 = time.perf_counter()
+            o2, i2, l2 = cache.lookup(batches[0][:2].contiguous())
+            q = batches[0][:2].cpu().numpy()
+            wid, wlen = COracleIndex(*ex.vocab_arrays()).match(q, nthreads=min(16, os.cpu_count() or 1))
+            hitm = wid >= 0
+            rows = table.storage[torch.from_numpy(wid[hitm].astype(np.int64)).to(dev)].cpu().numpy()
+            so = table.scale_offset
+            tab = {"int8": lambda: po.OracleTable("int8", D, rows[:, :D].view(np.int8), rows[:, so:so + 4].copy().view(np.float32)[:, 0]),
+                   "fp16": lambda: po.OracleTable("fp16", D, rows[:, :2 * D].view(np.float16)),
+                   "fp32": lambda: po.OracleTable("fp32", D, rows[:, :4 * D].view(np.float32)),
+                   "int4": lambda: po.OracleTable("int4", D, rows[:, :D // 2], rows[:, so:so + 2 * (D // table.group)].copy().view(np.float16), table.group)}[w["quant"]]()
+            want = np.empty(q.shape + (D,), dtype=np.uint16)
+            want[~hitm] = base.view(torch.int16).cpu().numpy().view(np.uint16)[q[~hitm]]
+            want[hitm] = po.cast_bits(tab.rows_fp32(np.arange(rows.shape[0])), "bf16")
+            ok = np.array_equal(wid, i2.cpu().numpy()) and np.array_equal(wlen, l2.cpu().numpy()) \
+                and np.array_equal(o2.view(torch.int16).cpu().numpy().view(np.uint16), want)
+            parity = {"result": "ok" if ok else "MISMATCH", "positions_checked": int(q.size), "seconds": time.perf_counter() - t0,
+                      "what": "fgram_id / match_len against oracle/c_oracle.c over the whole vocabulary, embeddings bit for bit against "
+                              "py_oracle's dequant + cast of the stored rows (or the fallback rows)"}
+        except Exception as e:
+            parity = {"result": "error: " + repr(e)}
+
     # ---- roofline ---------------------------------------------------------------------------------------------
     bpt = bytes_per_token(w, hit, probes, slot_bytes=index.slot_bytes)
     peak, peak_src = measured_peak_hbm()
@@ -513,7 +541,7 @@ def run_ours(args, w, rank, local_rank, world, name):
                    "l2": f"inputs > L2: {N_BATCHES} rotating id batches gather rows uniformly from a {table.bytes / 1e9:.2f} GB "
                          f"table and each step writes {T * D * 2 / 1e6:.0f} MB of output; no explicit flush",
                    "timing": "K steps captured in one CUDA graph, CUDA events on the launching stream, max over ranks"},
-        "e2e": e2e, "gpu_launches": int(gpu_launches), "clocks": clk, "roofline": roofline,
+        "e2e": e2e, "gpu_launches": int(gpu_launches), "clocks": clk, "roofline": roofline, "parity": parity,
     }
     if cpu_baseline is not None:
         line["cpu_baseline"] = cpu_baseline
@@ -796,6 +824,7 @@ def run_host(args, w, rank, local_rank, world):
     index = sb.FGramIndex(toks, lens)
     base = S.make_base_device(V, D, torch.bfloat16, seed=3, device=dev)
     batches = [S.make_stream_device(toks, lens, B, L, V, seed=100 + k, p_plant=1.0, pick_ids=longest) for k in range(4)]
+    h_vocab = (toks.cpu().numpy(), lens.cpu().numpy()) if not args.no_parity else None
     del toks, lens, longest
     out = torch.empty((B, L, D), dtype=torch.bfloat16, device=dev)
     out_id = torch.empty((B, L), dtype=torch.int32, device=dev)
@@ -806,6 +835,33 @@ def run_host(args, w, rank, local_rank, world):
 
     step(0)
     hit = float((out_id >= 0).float().mean().item())
+    # in-run parity: two batch rows of batch 0 against the oracle (ids / lengths from the C oracle over the whole vocabulary, rows
+    # from py_oracle's dequant of the host-resident bytes the kernel read)
+    parity = None
+    if h_vocab is not None:
+        try:
+            import numpy as np
+            from oracle import py_oracle as po
+            from oracle.c_oracle import COracleIndex
+            t0 = time.perf_counter()
+            q = batches[0][:2].cpu().numpy()
+            wid, wlen = COracleIndex(*h_vocab).match(q, nthreads=min(16, os.cpu_count() or 1))
+            hitm = wid >= 0
+            rows = table.storage[torch.from_numpy(wid[hitm].astype(np.int64))].numpy()
+            so = table.scale_offset
+            tab = {"int8": lambda: po.OracleTable("int8", D, rows[:, :D].view(np.int8), rows[:, so:so + 4].copy().view(np.float32)[:, 0]),
+                   "fp16": lambda: po.OracleTable("fp16", D, rows[:, :2 * D].view(np.float16)),
+                   "fp32": lambda: po.OracleTable("fp32", D, rows[:, :4 * D].view(np.float32)),
+                   "int4": lambda: po.OracleTable("int4", D, rows[:, :D // 2], rows[:, so:so + 2 * (D // table.group)].copy().view(np.float16), table.group)}[w["quant"]]()
+            want = np.empty(q.shape + (D,), dtype=np.uint16)
+            want[~hitm] = base.view(torch.int16).cpu().numpy().view(np.uint16)[q[~hitm]]
+            want[hitm] = po.cast_bits(tab.rows_fp32(np.arange(rows.shape[0])), "bf16")
+            got = out[:2].view(torch.int16).cpu().numpy().view(np.uint16)
+            ok = np.array_equal(wid, out_id[:2].cpu().numpy()) and np.array_equal(wlen, out_len[:2].cpu().numpy()) and np.array_equal(got, want)
+            parity = {"result": "ok" if ok else "MISMATCH", "positions_checked": int(q.size), "seconds": time.perf_counter() - t0}
+            del h_vocab
+        except Exception as e:
+            parity = {"result": "error: " + repr(e)}
     l0 = _lib.launch_count()
     with ClockSampler(local_rank) as clocks:
         ms = _timed_steps(step, steps, args.warmup, torch.cuda.synchronize, dev, 1, clocks=clocks, min_busy_s=0.3)
@@ -847,7 +903,7 @@ def run_host(args, w, rank, local_rank, world):
         "roofline": {"bound": "host_link", "achieved": link, "peak": HOST_LINK_PEAK_GBS, "unit": "GB/s", "frac": link / HOST_LINK_PEAK_GBS,
                      "traffic": None, "peak_source": "nominal PCIe Gen5 x16 per direction (host-link bound, not HBM)",
                      "host_link_GBps": link, "bytes_per_token_over_link": hit * stride},
-        "staged": staged_info,
+        "staged": staged_info, "parity": parity,
     }
     return line
 
@@ -871,7 +927,7 @@ def _child(args, name, steps, extra=(), timeout_s=600):
     if p.returncode != 0 or not lines:
         return {"error": f"rc={p.returncode}", "stderr_tail": p.stderr[-600:]}
     d = json.loads(lines[-1])
-    keep = {k: d.get(k) for k in ("value", "unit", "ms_per_step", "steps", "dtype", "gpu_launches", "clocks", "roofline", "e2e", "staged")
+    keep = {k: d.get(k) for k in ("value", "unit", "ms_per_step", "steps", "dtype", "gpu_launches", "clocks", "roofline", "e2e", "staged", "parity")
             if d.get(k) is not None}
     keep["config"] = d.get("config")
     keep["wall_seconds"] = wall
@@ -936,6 +992,7 @@ def main():
     ap.add_argument("--no-configs", action="store_true", help="suite at N = 1: skip the config 1 / 3 / 5 child runs")
     ap.add_argument("--no-sharded", action="store_true", help="suite at N > 1: skip the row-sharded config 4 part")
     ap.add_argument("--no-staged", action="store_true", help="config5: skip the staged variant")
+    ap.add_argument("--no-parity", action="store_true", help="config5: skip the in-run check against the oracle")
     ap.add_argument("--no-inputs-stable", action="store_true", help="do not pass SCONE_EMBED_INPUTS_STABLE in the device-timed steps")
     ap.add_argument("--sharded-timeout", type=float, default=600.0, help="suite at N > 1: seconds the config 4 part may take")
     ap.add_argument("--suite-seconds", type=float, default=660.0, help="suite at N = 1: wall-clock budget shared by the child runs")

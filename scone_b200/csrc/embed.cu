@@ -44,6 +44,7 @@ static int dispatch(int P, EmbedParams &p, int quant, int out_dtype, cudaStream_
     if (const char *e = getenv("SCONE_EMBED_P")) P = atoi(e) > P ? atoi(e) : P;
     if (const char *e = getenv("SCONE_STAGGER_NS")) p.stagger_ns = atoi(e);
     if (const char *e = getenv("SCONE_STAGGER_CTA_NS")) p.stagger_cta_ns = atoi(e);
+    if (const char *e = getenv("SCONE_BASE_POLICY")) p.base_policy = atoi(e);
 #endif
     if (p.additive && P < 4) P = 4;  // see launch_p
     // Two kernels (measured, profiles/tune_r02.md): the plain path runs fastest on embed_bulk_kernel (one ring, the matcher

@@ -58,6 +58,7 @@ struct EmbedParams {
     int32_t stagger_ns;   // matcher warp w starts its first probes w * stagger_ns later (0 = together)
     int32_t stagger_cta_ns;  // ... and the c-th CTA of an SM (blockIdx / #SMs) another c * stagger_cta_ns later
     uint32_t flags;          // SCONE_EMBED_* of scone_embed_opts_t
+    int32_t base_policy;     // L2 policy of the fallback / base rows: 0 evict-first (streamed), 1 default, 2 evict-last (kept)
 };
 
 // row bytes holding 8 consecutive elements of a stored row
@@ -77,6 +78,15 @@ __device__ __forceinline__ const uint8_t *row_ptr(const EmbedParams &p, int32_t 
 
 constexpr int kRing = 16;  // tiles the matchers may run ahead of the gather warps
 constexpr uint32_t kEmbedPipe = 1u << 31;  // EmbedParams::flags, internal: use embed_pipe_kernel instead of embed_bulk_kernel
+
+// L2 policy for the fallback / base rows (EmbedParams::base_policy)
+__device__ __forceinline__ uint64_t base_row_policy(int which) {
+    uint64_t pol;
+    if (which == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    else if (which == 1) asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+    else asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
 
 // programmatic dependent launch: block until the grid this one was launched behind has completed and its writes are visible
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
@@ -460,6 +470,7 @@ __global__ void __launch_bounds__(32 * (NM + NG), MINB) embed_bulk_kernel(const 
         const int j = lane / P;
         const int back = p.ix.max_n - 1;
         const uint64_t pol = policy_evict_first();
+        const uint64_t pol_base = base_row_policy(p.base_policy);
         int64_t it = warp;
         int64_t tile = blockIdx.x + it * gridDim.x;
         int32_t wtok = -1;
@@ -531,9 +542,9 @@ __global__ void __launch_bounds__(32 * (NM + NG), MINB) embed_bulk_kernel(const 
             if (lane == 0) mbar_arrive_expect_tx(&full_bar[q], total);
             __syncwarp();
             uint8_t *slot = rows_smem + (size_t)(q * G + j) * lay.slot_bytes;
-            if (bytes) bulk_g2s(slot, src, bytes, &full_bar[q], pol);
+            if (bytes) bulk_g2s(slot, src, bytes, &full_bar[q], fid >= 0 ? pol : pol_base);
             if (src2) bulk_g2s(slot + lay.pos_off, src2, (uint32_t)p.D * 2u, &full_bar[q], policy_evict_last());
-            if (src3) bulk_g2s(slot + add_off, src3, (uint32_t)p.D * 2u, &full_bar[q], pol);
+            if (src3) bulk_g2s(slot + add_off, src3, (uint32_t)p.D * 2u, &full_bar[q], pol_base);
             SCONE_STAMP(3, warp == 0 && lane == 0 && it == 0);                        // first bulk copies issued
             // the match result is this warp's only global write: after the previous grid (see `early` above)
             if (!waited) {

@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(32 * (NM + NL + NG), MINB) embed_pipe_kernel(c
     } else if (warp < NM + NL) {
         // ===== loader warps: tiles in order; lane g of loader g % NL stages position g of the tile =====
         const int ld = warp - NM;
-        const uint64_t pol = policy_evict_first(), pol_keep = policy_evict_last();
+        const uint64_t pol = policy_evict_first(), pol_keep = policy_evict_last(), pol_base = base_row_policy(p.base_policy);
         int64_t itl = 0;
         for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++itl) {
             const int ms = (int)(itl % MR), q = (int)(itl % R);
@@ -175,9 +175,9 @@ __global__ void __launch_bounds__(32 * (NM + NL + NG), MINB) embed_pipe_kernel(c
             if (lane == 0) mbar_arrive_expect_tx(&full_bar[q], total);
             __syncwarp();
             uint8_t *slot = rows_smem + (size_t)(q * G + lane) * lay.slot_bytes;
-            if (bytes) bulk_g2s(slot, src, bytes, &full_bar[q], pol);
+            if (bytes) bulk_g2s(slot, src, bytes, &full_bar[q], e.x >= 0 ? pol : pol_base);
             if (src2) bulk_g2s(slot + lay.pos_off, src2, (uint32_t)p.D * 2u, &full_bar[q], pol_keep);
-            if (src3) bulk_g2s(slot + add_off, src3, (uint32_t)p.D * 2u, &full_bar[q], pol);
+            if (src3) bulk_g2s(slot + add_off, src3, (uint32_t)p.D * 2u, &full_bar[q], pol_base);
         }
     } else {
         // ===== gather warps: every warp waits for and releases every tile, in order =====

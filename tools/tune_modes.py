@@ -19,7 +19,7 @@ import scone_b200 as sb  # noqa: E402
 from scone_b200.utils import synthetic as S  # noqa: E402
 from tune_embed import graph_time  # noqa: E402
 
-KNOBS = ("SCONE_HINT", "SCONE_EMBED_VARIANT", "SCONE_EMBED_P", "SCONE_STAGGER_NS", "SCONE_STAGGER_CTA_NS", "SCONE_EMBED_PIPE")
+KNOBS = ("SCONE_HINT", "SCONE_EMBED_VARIANT", "SCONE_EMBED_P", "SCONE_STAGGER_NS", "SCONE_STAGGER_CTA_NS", "SCONE_EMBED_PIPE", "SCONE_BASE_POLICY")
 
 
 def main():
