@@ -282,7 +282,7 @@ int scone_host_gather_rows(const void *h_rows, int64_t row_stride, int64_t num_r
 
 /* ---- host-fed pipeline ----------------------------------------------------------------------------------
  * The throughput form of scone_embed_forward for callers whose ids live in HOST memory (the reference's engine
- * tokenises on the host, scone/inference/engine.py:222-233): `slots` batches rotate through three streams owned by
+ * tokenises on the host, scone/inference/engine.py:222-233): `slots` batches rotate through the streams owned by
  * the pipeline -- copy-in (pinned host ids -> HBM), compute (the fused kernel), copy-out (match result -> pinned
  * host) -- chained per slot with events, so batch k+1's H2D and batch k-1's D2H run under batch k's kernel.
  * All buffers are the caller's: per slot d_ids int64 [B*L], d_out [B*L*D] out_dtype, d_meta / h_meta 5*B*L bytes
@@ -296,7 +296,7 @@ int scone_pipeline_create(const scone_index_t *index, const scone_table_desc_t *
  * been waited for yet, the call waits for it first.  Returns without waiting for the new batch: h_ids_pinned is read by an
  * asynchronous copy and must stay untouched until scone_pipeline_wait(slot) has returned. */
 int scone_pipeline_submit(scone_pipeline_t *p, const int64_t *h_ids_pinned, int32_t *slot);
-/* The pipeline runs on three streams of its own, ordered against the caller only at creation.  After changing anything
+/* The pipeline runs on streams of its own (copy-in, two alternating compute streams, copy-out), ordered against the caller only at creation.  After changing anything
  * the pipeline reads (table rows, base / position embeddings) on `stream`, call this before the next submit: every batch
  * submitted afterwards runs behind the work already enqueued on `stream`. */
 int scone_pipeline_follow(scone_pipeline_t *p, void *stream);

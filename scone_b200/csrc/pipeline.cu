@@ -19,7 +19,10 @@ struct Pipeline {
     int32_t slots;
     std::vector<void *> d_ids, d_out, d_meta, h_meta;
     uint32_t *status;
-    cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
+    // two compute streams, used alternately: consecutive batches write different slots, so their kernels are independent and
+    // batch k+1's CTAs move onto the SMs as batch k's retire (one stream would serialise them: the event record / waits between
+    // two launches of a stream also end the programmatic-dependent-launch overlap, and each batch would cost an isolated launch)
+    cudaStream_t s_in = nullptr, s_run[2] = {nullptr, nullptr}, s_out = nullptr;
     std::vector<cudaEvent_t> ev_in, ev_run, ev_out;
     std::vector<char> busy;
     int64_t k = 0;
@@ -30,7 +33,8 @@ static void pipeline_free(Pipeline *p) {
     for (auto e : p->ev_run) cudaEventDestroy(e);
     for (auto e : p->ev_out) cudaEventDestroy(e);
     if (p->s_in) cudaStreamDestroy(p->s_in);
-    if (p->s_run) cudaStreamDestroy(p->s_run);
+    for (int i = 0; i < 2; ++i)
+        if (p->s_run[i]) cudaStreamDestroy(p->s_run[i]);
     if (p->s_out) cudaStreamDestroy(p->s_out);
     delete p;
 }
@@ -85,7 +89,8 @@ int scone_pipeline_create(const scone_index_t *index, const scone_table_desc_t *
     };
     cudaError_t e;
     if ((e = cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
-    if ((e = cudaStreamCreateWithFlags(&p->s_run, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
+    for (int i = 0; i < 2; ++i)
+        if ((e = cudaStreamCreateWithFlags(&p->s_run[i], cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
     if ((e = cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
     for (int s = 0; s < slots; ++s) {
         cudaEvent_t a, b, c;
@@ -111,20 +116,19 @@ int scone_pipeline_submit(scone_pipeline_t *pp, const int64_t *h_ids_pinned, int
     SCONE_CUDA(cudaMemcpyAsync(p->d_ids[s], h_ids_pinned, (size_t)T * 8, cudaMemcpyHostToDevice, p->s_in));
     SCONE_CUDA(cudaEventRecord(p->ev_in[s], p->s_in));
     // compute: after the ids are in and the slot's previous results have left the device
-    SCONE_CUDA(cudaStreamWaitEvent(p->s_run, p->ev_in[s], 0));
-    SCONE_CUDA(cudaStreamWaitEvent(p->s_run, p->ev_out[s], 0));
+    cudaStream_t run = p->s_run[p->k & 1];
+    SCONE_CUDA(cudaStreamWaitEvent(run, p->ev_in[s], 0));
+    SCONE_CUDA(cudaStreamWaitEvent(run, p->ev_out[s], 0));
     uint8_t *meta = static_cast<uint8_t *>(p->d_meta[s]);
-    // The kernel that precedes this one on s_run is the pipeline's own previous batch, which writes only another slot's
+    // The kernel that precedes this one on its stream is the pipeline's own batch k-2, which writes only another slot's
     // outputs; this batch's ids arrive by the copy above (an event dependency, not a kernel) and the tables are static
-    // while the pipeline runs (scone_pipeline_follow orders it behind a caller's update): SCONE_EMBED_INPUTS_STABLE holds,
-    // so consecutive batches overlap -- batch k+1 matches and fetches rows under batch k's tail.
+    // while the pipeline runs (scone_pipeline_follow orders it behind a caller's update): SCONE_EMBED_INPUTS_STABLE holds.
     scone_embed_opts_t opts{};
     opts.flags = SCONE_EMBED_INPUTS_STABLE;
     int rc = scone_embed_forward_ex(p->index, &p->table, p->base, p->base_rows, p->pos, static_cast<const int64_t *>(p->d_ids[s]), p->B,
-                                    p->L, p->d_out[s], p->out_dtype, reinterpret_cast<int32_t *>(meta), meta + 4 * T, p->status, &opts,
-                                    p->s_run);
+                                    p->L, p->d_out[s], p->out_dtype, reinterpret_cast<int32_t *>(meta), meta + 4 * T, p->status, &opts, run);
     if (rc != SCONE_OK) return rc;
-    SCONE_CUDA(cudaEventRecord(p->ev_run[s], p->s_run));
+    SCONE_CUDA(cudaEventRecord(p->ev_run[s], run));
     // copy-out
     SCONE_CUDA(cudaStreamWaitEvent(p->s_out, p->ev_run[s], 0));
     SCONE_CUDA(cudaMemcpyAsync(p->h_meta[s], p->d_meta[s], (size_t)T * 5, cudaMemcpyDeviceToHost, p->s_out));
@@ -142,7 +146,8 @@ int scone_pipeline_follow(scone_pipeline_t *pp, void *stream) {
     SCONE_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     cudaError_t e = cudaEventRecord(ev, (cudaStream_t)stream);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(p->s_in, ev, 0);
-    if (e == cudaSuccess) e = cudaStreamWaitEvent(p->s_run, ev, 0);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(p->s_run[0], ev, 0);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(p->s_run[1], ev, 0);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(p->s_out, ev, 0);
     cudaEventDestroy(ev);  // released once the recorded work has completed
     if (e != cudaSuccess) {
@@ -166,7 +171,8 @@ int scone_pipeline_destroy(scone_pipeline_t *pp) {
     if (!pp) return SCONE_OK;
     Pipeline *p = reinterpret_cast<Pipeline *>(pp);
     cudaStreamSynchronize(p->s_in);
-    cudaStreamSynchronize(p->s_run);
+    cudaStreamSynchronize(p->s_run[0]);
+    cudaStreamSynchronize(p->s_run[1]);
     cudaStreamSynchronize(p->s_out);
     pipeline_free(p);
     return SCONE_OK;

@@ -1,6 +1,6 @@
 """Host-fed lookups, multi-buffered: ids arrive in pinned HOST memory, match results go back to the host, and the
 copies of neighbouring batches overlap the kernel.  Thin wrapper over the native ``scone_pipeline_*`` runtime
-(``csrc/pipeline.cu``: three streams, per-slot events, ``cudaMemcpyAsync`` in and out around the fused kernel).
+(``csrc/pipeline.cu``: a copy-in stream, two alternating compute streams, a copy-out stream, per-slot events, ``cudaMemcpyAsync`` in and out around the fused kernel).
 
     pipe = HostPipeline(index, table, base_emb, batch_shape=(B, L))
     for h_ids in batches:                       # pinned int64 [B, L] tensors
@@ -71,7 +71,7 @@ class HostPipeline:
 
     def follow(self, stream: Optional[torch.cuda.Stream] = None) -> None:
         """Order every batch submitted from now on behind the work already enqueued on ``stream`` (default: the current
-        stream).  The pipeline runs on its own three streams and is ordered against the caller only at construction, so
+        stream).  The pipeline runs on its own streams and is ordered against the caller only at construction, so
         call this after updating anything it reads -- ``table.store`` / ``cache_embeddings`` / ``set_base_embedding``."""
         st = stream if stream is not None else torch.cuda.current_stream(self.index.device)
         _lib.check(_lib.load().scone_pipeline_follow(self._h, st.cuda_stream))
