@@ -297,3 +297,44 @@ def test_bench_byte_accounting_matches_the_survey_formula():
     assert b.bytes_per_token(w2, 1.0, 4, slot_bytes=16) == 8 + 64 + 1028 + 2048 + 5 == 3153
     assert b.bytes_per_token(w3, 1.0, 5, slot_bytes=16) == 8 + 80 + 2112 + 8192 + 5 == 10397
     assert b.bytes_per_token(w2, 0.75, 3) == 8 + 96 + 0.75 * 1028 + 0.25 * 2048 + 2048 + 5
+
+
+def test_compact20_slot_packing_is_injective():
+    """numpy restatement of common.cuh::pack_key20 (a 28-bit id + five 20-bit tokens, reverse order, 0xFFFFF padded, in 16 bytes):
+    the four words determine (length, tokens) uniquely and the id survives next to the four spare token bits; the all-ones word
+    that marks an empty slot cannot be produced by a valid entry (ids < 2^28 - 1)."""
+    PAD = 0xFFFFF
+    rng = np.random.default_rng(20)
+
+    def pack(fid, toks_rev):
+        t = [int(x) for x in toks_rev] + [PAD] * (5 - len(toks_rev))
+        w0 = (fid & 0x0FFFFFFF) | ((t[0] & 0xF) << 28)
+        w1 = (t[0] >> 4) | ((t[1] & 0xFFFF) << 16)
+        w2 = (t[1] >> 16) | (t[2] << 4) | ((t[3] & 0xFF) << 24)
+        w3 = (t[3] >> 8) | (t[4] << 12)
+        assert max(w0, w1, w2, w3) < 2 ** 32
+        return w0, w1, w2, w3
+
+    def unpack(w):
+        w0, w1, w2, w3 = w
+        t0 = (w0 >> 28) | ((w1 & 0xFFFF) << 4)
+        t1 = (w1 >> 16) | ((w2 & 0xF) << 16)
+        t2 = (w2 >> 4) & PAD
+        t3 = (w2 >> 24) | ((w3 & 0xFFF) << 8)
+        t4 = w3 >> 12
+        toks = [t for t in (t0, t1, t2, t3, t4)]
+        while toks and toks[-1] == PAD:
+            toks.pop()
+        return w0 & 0x0FFFFFFF, toks
+
+    seen = {}
+    for _ in range(20000):
+        n = int(rng.integers(1, 6))
+        toks = rng.integers(0, PAD, size=n).tolist()              # valid tokens are < 0xFFFFF
+        fid = int(rng.integers(0, 2 ** 28 - 1))
+        w = pack(fid, toks)
+        assert w[0] != 0xFFFFFFFF
+        assert unpack(w) == (fid, toks)
+        key = (w[0] >> 28, w[1], w[2], w[3])
+        assert seen.setdefault(key, toks) == toks                 # equal key words <=> equal (length, tokens)
+    assert pack(2 ** 28 - 2, [PAD - 1] * 5)[0] != 0xFFFFFFFF

@@ -347,3 +347,29 @@ def test_hypothesis_dequant_py_vs_c(seed, quant, out_dtype):
     out, fid, _, err = cix.embed(quant, D, 128, packed, stride, packed[:, soff:] if soff else None, stride, base, q, out_dtype)
     assert err == 0 and fid.tolist() == [[0, 1, 2, 3, 4, -1]]
     assert np.array_equal(out[0, :5], po.cast_bits(tab.rows_fp32(np.arange(5)), out_dtype))
+
+
+def test_fold_projection_contract():
+    """oracle/py_oracle.py::fold_projection -- the reference's bias-free f_gram_projection (language_model.py:172-176, :236)
+    on bf16-rounded inputs: the stated bound must hold for fp32 accumulation in ANY order (forward, reverse, pairwise, blocked),
+    because the tensor cores' order is unspecified; and torch's own Linear on the rounded inputs lands inside it too."""
+    import torch
+    rng = np.random.default_rng(3)
+    rows = (rng.standard_normal((37, 384)) * 0.5).astype(np.float32)
+    W = (rng.standard_normal((96, 384)) / np.sqrt(384)).astype(np.float32)
+    P, bound = po.fold_projection(rows, W)
+    a, w = po.round_to_bf16(rows), po.round_to_bf16(W)
+    assert np.array_equal(po.round_to_bf16(a), a) and np.abs(a - rows).max() <= np.abs(rows).max() * 2.0 ** -8
+    prods = a[:, None, :] * w[None, :, :]                       # exact in fp32: 8-bit x 8-bit significands
+    fwd = np.zeros((37, 96), np.float32)
+    for k in range(384):
+        fwd = (fwd + prods[:, :, k]).astype(np.float32)
+    rev = np.zeros((37, 96), np.float32)
+    for k in range(383, -1, -1):
+        rev = (rev + prods[:, :, k]).astype(np.float32)
+    blocked = prods.reshape(37, 96, 24, 16).sum(axis=3, dtype=np.float32).sum(axis=2, dtype=np.float32)
+    for x in (fwd, rev, blocked, prods.sum(axis=2, dtype=np.float32)):
+        assert np.all(np.abs(x - P) <= bound)
+    lin = torch.nn.functional.linear(torch.from_numpy(a), torch.from_numpy(w)).numpy()         # the reference's op (fp32 Linear)
+    assert np.all(np.abs(lin - P) <= bound)
+    assert bound.max() < 1e-4 * np.abs(P).max()                 # ... and it is tight enough to mean something
