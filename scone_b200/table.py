@@ -86,7 +86,7 @@ class CacheTable:
         buf = (C.c_uint8 * nbytes).from_address(host.value)
         t = torch.frombuffer(buf, dtype=torch.uint8)
         self._host_dev_ptr = dev.value
-        self._host_region = (host.value, nbytes)
+        # the region lives as long as this table: ``storage`` (and numpy views of it) must not outlive the CacheTable
         weakref.finalize(self, _free_host, host.value, nbytes)
         return t
 
