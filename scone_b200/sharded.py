@@ -10,7 +10,9 @@ New design (the reference's inference path is single-process, single-GPU; SURVEY
   * each owner copies the requested rows VERBATIM -- still quantised -- into a reply buffer (``gather_packed``);
   * all-to-all #2 carries the packed rows back (INT4: 2 112 B instead of 8 192 B per row over NVLink);
   * the requester dequantises the received rows, fills misses from its local fallback table and writes
-    ``[B, L, D]`` in one ``scone_embed_gather`` launch.  Misses never leave the GPU.
+    ``[B, L, D]`` with ``scone_embed_gather``.  Misses never leave the GPU.
+  The batch is cut into micro-batches of batch rows and these steps are software-pipelined: all-to-all #2 of one
+  micro-batch overlaps the owner-side gather of the next and the dequantising gather of the previous one.
 
 The routing arithmetic is plain torch (device-agnostic, exercised on CPU with gloo in tests/test_sharded_cpu.py); the
 three compute steps are CUDA kernels of libscone_b200 behind the ``ops`` object.
@@ -40,43 +42,63 @@ def shard_rows(num_fgrams: int, rank: int, world: int) -> int:
 
 @dataclass
 class RoutePlan:
-    order: torch.Tensor          # [n_hit] flat positions of the hits, grouped by owner (stable)
-    send_rows: torch.Tensor      # [n_hit] int32 local row numbers, same order
-    send_counts: List[int]       # requests this rank sends to each owner
-    recv_counts: List[int]       # requests this rank receives from each requester
-    slot_of_position: torch.Tensor  # [T] int32: index into the reply buffer, -1 for a miss
+    """Routing of one batch, cut into ``micro`` micro-batches of whole batch rows."""
+    micro: int                       # number of micro-batches
+    bounds: List[Tuple[int, int]]    # [micro] (first position, end position) of each micro-batch in the flattened batch
+    order: torch.Tensor              # [n_hit] flat positions of the hits, grouped by (micro-batch, owner), stable
+    send_rows: torch.Tensor          # [n_hit] int32 local row numbers, same order
+    send_counts: List[List[int]]     # [micro][W] requests this rank sends to each owner
+    recv_counts: List[List[int]]     # [micro][W] requests this rank receives from each requester
+    slot_of_position: torch.Tensor   # [T] int32: index into ITS micro-batch's reply buffer, -1 for a miss
+
+    def send_offset(self, m: int) -> int:
+        return sum(sum(c) for c in self.send_counts[:m])
 
 
-def make_plan(fgram_id: torch.Tensor, world: int, group=None) -> RoutePlan:
-    """Bucket the hit positions by owner and exchange the bucket sizes (the one host synchronisation of the tier)."""
+def make_plan(fgram_id: torch.Tensor, world: int, group=None, micro: int = 1) -> RoutePlan:
+    """Bucket the hit positions by (micro-batch, owner) with ONE stable sort and exchange all bucket sizes with ONE small
+    all-to-all (the tier's one host synchronisation per batch)."""
+    B = fgram_id.shape[0] if fgram_id.dim() == 2 else 1
     flat = fgram_id.reshape(-1)
     T = flat.numel()
+    L = T // max(B, 1)
+    micro = max(1, min(int(micro), B))
+    rows_per = max(1, (B + micro - 1) // micro)
+    micro = max(1, (B + rows_per - 1) // rows_per)
+    bounds = [(m * rows_per * L, min(B, (m + 1) * rows_per) * L) for m in range(micro)]
     hit = flat >= 0
-    key = torch.where(hit, owner_of(flat.clamp(min=0), world), torch.full_like(flat, world))
+    mb = torch.div(torch.arange(T, device=flat.device), max(rows_per * L, 1), rounding_mode="floor")
+    key = torch.where(hit, mb * world + owner_of(flat.clamp(min=0), world), torch.full_like(mb, micro * world))
     order_all = torch.argsort(key, stable=True)
-    counts = torch.bincount(key, minlength=world + 1)[:world]
+    counts = torch.bincount(key, minlength=micro * world + 1)[:micro * world].view(micro, world)
     n_hit = int(counts.sum().item())
     order = order_all[:n_hit]
     send_rows = local_row_of(flat[order], world).to(torch.int32)
-    recv = torch.empty_like(counts)
-    dist.all_to_all_single(recv, counts, group=group)
+    send_t = counts.t().contiguous()                 # [W, micro]: what goes to each owner, per micro-batch
+    recv_t = torch.empty_like(send_t)                # [W, micro]: what each requester asks of this rank
+    dist.all_to_all_single(recv_t, send_t, group=group)
+    # position -> slot in its micro-batch's reply buffer
+    first_of_mb = torch.cumsum(counts.sum(dim=1), 0) - counts.sum(dim=1)
     slot = torch.full((T,), -1, dtype=torch.int32, device=flat.device)
-    slot[order] = torch.arange(n_hit, dtype=torch.int32, device=flat.device)
-    return RoutePlan(order, send_rows, counts.tolist(), recv.tolist(), slot)
+    slot[order] = (torch.arange(n_hit, device=flat.device) - first_of_mb[mb[order]]).to(torch.int32)
+    return RoutePlan(micro, bounds, order, send_rows, counts.tolist(), recv_t.t().tolist(), slot)
 
 
-def exchange_requests(plan: RoutePlan, group=None) -> torch.Tensor:
-    """all-to-all #1: local row numbers to their owners.  Returns the int32 rows this rank must serve."""
-    req = torch.empty((sum(plan.recv_counts),), dtype=torch.int32, device=plan.send_rows.device)
-    dist.all_to_all_single(req, plan.send_rows, plan.recv_counts, plan.send_counts, group=group)
-    return req
+def exchange_requests(plan: RoutePlan, m: int = 0, group=None, async_op: bool = False):
+    """all-to-all #1 of micro-batch m: local row numbers to their owners.  Returns the int32 rows this rank must serve
+    (and the work handle when ``async_op``)."""
+    off = plan.send_offset(m)
+    send = plan.send_rows[off:off + sum(plan.send_counts[m])]
+    req = torch.empty((sum(plan.recv_counts[m]),), dtype=torch.int32, device=send.device)
+    work = dist.all_to_all_single(req, send, plan.recv_counts[m], plan.send_counts[m], group=group, async_op=async_op)
+    return (req, work) if async_op else req
 
 
-def exchange_replies(plan: RoutePlan, served: torch.Tensor, group=None) -> torch.Tensor:
-    """all-to-all #2: packed rows back to the requesters, in request order.  served: [n_recv, row_stride] uint8."""
-    reply = torch.empty((sum(plan.send_counts), served.shape[1]), dtype=served.dtype, device=served.device)
-    dist.all_to_all_single(reply, served, plan.send_counts, plan.recv_counts, group=group)
-    return reply
+def exchange_replies(plan: RoutePlan, served: torch.Tensor, m: int = 0, group=None, async_op: bool = False):
+    """all-to-all #2 of micro-batch m: packed rows back to the requesters, in request order.  served: [n_recv, row_stride] uint8."""
+    reply = torch.empty((sum(plan.send_counts[m]), served.shape[1]), dtype=served.dtype, device=served.device)
+    work = dist.all_to_all_single(reply, served, plan.send_counts[m], plan.recv_counts[m], group=group, async_op=async_op)
+    return (reply, work) if async_op else reply
 
 
 class CudaOps:
@@ -100,27 +122,52 @@ class CudaOps:
 
 
 class ShardedEmbeddingCache:
-    """``lookup`` over a table row-sharded across the process group.
+    """``lookup`` over a table row-sharded across the process group, through two all-to-alls (the north star's design).
 
     ``ops`` supplies match / serve / assemble; the default is :class:`CudaOps` (there is no CPU implementation in the
     product -- tests inject an oracle-backed stand-in to exercise the routing on CPU with gloo).
+
+    The batch is cut into ``micro_batches`` groups of batch rows and software-pipelined: while the packed rows of
+    micro-batch m cross NVLink (all-to-all #2, on the communicator's own stream), the owner-side gather of micro-batch m+1
+    and the requester-side dequantising gather of micro-batch m-1 run on the compute stream.  One stable sort buckets the
+    whole batch by (micro-batch, owner) and one small all-to-all exchanges every bucket size: one host synchronisation.
     """
 
-    def __init__(self, ops, group=None):
+    def __init__(self, ops, group=None, micro_batches: int = 4):
         self.ops = ops
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
+        self.micro_batches = max(1, int(micro_batches))
         self.last_plan: Optional[RoutePlan] = None
 
     def lookup(self, input_ids: torch.Tensor, out: Optional[torch.Tensor] = None):
         fgram_id, match_len = self.ops.match(input_ids)
-        plan = make_plan(fgram_id, self.world, self.group)
-        requests = exchange_requests(plan, self.group)
-        served = self.ops.serve(requests)
-        reply = exchange_replies(plan, served, self.group)
-        embeds = self.ops.assemble(input_ids, reply, plan.slot_of_position, out)
+        B, L = input_ids.shape
+        plan = make_plan(fgram_id, self.world, self.group, micro=self.micro_batches)
         self.last_plan = plan
+        M = plan.micro
+        slot2d = plan.slot_of_position.view(B, L)
+        # all-to-all #1 of every micro-batch (a few bytes per position): issued at once, waited for just before its serve
+        reqs = [exchange_requests(plan, m, self.group, async_op=True) for m in range(M)]
+        parts, replies = [None] * M, [None] * M
+
+        def assemble(m):
+            b0, b1 = plan.bounds[m][0] // L, plan.bounds[m][1] // L
+            reply, work = replies[m]
+            work.wait()
+            res = self.ops.assemble(input_ids[b0:b1], reply, slot2d[b0:b1].reshape(-1), None if out is None else out[b0:b1])
+            parts[m] = res
+
+        for m in range(M):
+            req, work = reqs[m]
+            work.wait()
+            served = self.ops.serve(req)                                     # owner side: packed rows, no dequantisation
+            replies[m] = exchange_replies(plan, served, m, self.group, async_op=True)   # crosses NVLink while ...
+            if m >= 1:
+                assemble(m - 1)                                             # ... the previous micro-batch is dequantised
+        assemble(M - 1)
+        embeds = out if out is not None else (parts[0] if M == 1 else torch.cat(parts, dim=0))
         return embeds, fgram_id, match_len
 
 

@@ -46,7 +46,7 @@ for quant, D, max_n in (("int4", 4096, 5), ("fp16", 1024, 3), ("int8", 2048, 4))
     torch.cuda.synchronize()
     got = emb.view(torch.int16).cpu().numpy().view(np.uint16)
     good = np.array_equal(got, want) and np.array_equal(fid.cpu().numpy(), wid) and np.array_equal(ml.cpu().numpy(), wlen)
-    print(f"rank {rank}/{world} {quant} D={D}: {'OK' if good else 'MISMATCH'} hits={int((wid >= 0).sum())} sent={cache.last_plan.send_counts}", flush=True)
+    print(f"rank {rank}/{world} {quant} D={D}: {'OK' if good else 'MISMATCH'} hits={int((wid >= 0).sum())} micro-batches={cache.last_plan.micro} sent={[sum(c) for c in zip(*cache.last_plan.send_counts)]}", flush=True)
     ok = ok and good
     # peer-direct variant: one kernel, rows pulled over NVLink from symmetric memory
     pt = sharded.PeerShardedTable(N, D, quant, device=dev)

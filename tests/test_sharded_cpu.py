@@ -50,7 +50,11 @@ class OracleOps:
         if hit.any():
             res[hit] = po.cast_bits(tab.rows_fp32(slot[hit]), self.out_dtype)
         res[~hit] = self.base_bits[ids[~hit]]
-        return torch.from_numpy(res.reshape(tuple(input_ids.shape) + (D,)).view(np.int16))
+        res_t = torch.from_numpy(res.reshape(tuple(input_ids.shape) + (D,)).view(np.int16))
+        if out is not None:                      # like CudaOps.assemble: the caller's buffer is written in place
+            out.copy_(res_t)
+            return out
+        return res_t
 
 
 def _worker(rank, world, port, quant, ret):
@@ -75,12 +79,19 @@ def _worker(rank, world, port, quant, ret):
         q = S.make_stream_numpy(toks, lens, B, L, V, seed=100 + rank)    # each rank has its own batch
         cache = sharded.ShardedEmbeddingCache(OracleOps(toks, lens, local, (quant, D, soff), base_bits, "bf16"))
         emb, fid, ml = cache.lookup(torch.from_numpy(q))
+        assert cache.last_plan.micro == 3                              # B = 3 rows: three micro-batches, pipelined
+        one = sharded.ShardedEmbeddingCache(cache.ops, micro_batches=1)
+        emb1, fid1, _ = one.lookup(torch.from_numpy(q))                 # ... and the unpipelined form gives the same result
+        assert one.last_plan.micro == 1 and torch.equal(emb1, emb) and torch.equal(fid1, fid)
+        pre = torch.zeros_like(emb)
+        emb2, _, _ = cache.lookup(torch.from_numpy(q), out=pre)         # caller-provided output, written per micro-batch
+        assert emb2 is pre and torch.equal(pre, emb)
         got = emb.numpy().view(np.uint16)
         want, wid, wlen, err = COracleIndex(toks, lens).embed(quant, D, 128, packed, stride, packed[:, soff:] if soff else None,
                                                               stride, base_bits, q, "bf16")
         ok = err == 0 and np.array_equal(got, want) and np.array_equal(fid.numpy(), wid) and np.array_equal(ml.numpy(), wlen)
         plan = cache.last_plan
-        ok = ok and sum(plan.send_counts) == int((wid >= 0).sum()) and min(plan.send_counts) > 0
+        ok = ok and sum(sum(c) for c in plan.send_counts) == int((wid >= 0).sum()) and min(sum(c) for c in zip(*plan.send_counts)) > 0
         # a batch with no hits at all, and one where every hit goes to one owner
         none = torch.full((2, 9), V - 1, dtype=torch.long)
         e2, f2, _ = cache.lookup(none)
