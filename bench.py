@@ -700,8 +700,8 @@ def run_sharded(args, w, rank, local_rank, world, modes=("peer", "nccl"), parity
             "value": world * T / step_s, "unit": "tokens/s", "tokens_per_s_per_gpu": T / step_s, "ms_per_step": ms / steps,
             "gpu_launches_per_step": int(launches_per_step), "clocks": clk,
             "exchange": ("rows pulled from peer memory over NVLink inside the fused kernel (TMA bulk, no collective call)" if mode == "peer"
-                         else f"NCCL: all-to-all of int32 row numbers, owner-side packed gather, all-to-all of packed rows, local dequant; "
-                              f"software-pipelined over {args.nccl_micro} micro-batches of batch rows"),
+                         else f"NCCL: all-to-all of int32 row numbers, owner-side packed gather, all-to-all of packed rows, local dequant"
+                              + (f"; software-pipelined over {args.nccl_micro} micro-batches of batch rows" if args.nccl_micro > 1 else "")),
             "nvlink": {"achieved_in_GBps_per_gpu": nv_in, "peak": NVLINK_PEAK_GBS, "frac": nv_in / NVLINK_PEAK_GBS,
                        "peak_source": "B200_PROFILING.md measured peer copy, per direction per GPU",
                        "bytes_in_per_step_per_gpu": remote * table.row_stride},
@@ -1001,7 +1001,7 @@ def main():
                     help="distribution of the planted f-gram ids over the table: uniform (primary, worst case for caches) or Zipf-like")
     ap.add_argument("--rows-per-gpu", type=int, default=0, help="config4/5: table rows per GPU (default: the named size / what host RAM allows)")
     ap.add_argument("--sharded-mode", default="both", choices=["both", "peer", "nccl"], help="config4: which exchange variants to run")
-    ap.add_argument("--nccl-micro", type=int, default=4, help="config4, NCCL variant: micro-batches the two all-to-alls are pipelined over")
+    ap.add_argument("--nccl-micro", type=int, default=1, help="config4, NCCL variant: micro-batches the two all-to-alls are pipelined over")
     ap.add_argument("--host-fraction", type=float, default=0.0, help="config5: fraction of host RAM to pin (default 0.5)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -11,8 +11,8 @@ New design (the reference's inference path is single-process, single-GPU; SURVEY
   * all-to-all #2 carries the packed rows back (INT4: 2 112 B instead of 8 192 B per row over NVLink);
   * the requester dequantises the received rows, fills misses from its local fallback table and writes
     ``[B, L, D]`` with ``scone_embed_gather``.  Misses never leave the GPU.
-  The batch is cut into micro-batches of batch rows and these steps are software-pipelined: all-to-all #2 of one
-  micro-batch overlaps the owner-side gather of the next and the dequantising gather of the previous one.
+  Optionally the batch is cut into micro-batches of batch rows and these steps are software-pipelined (measured: no gain on
+  8 GPUs, see ``ShardedEmbeddingCache``).
 
 The routing arithmetic is plain torch (device-agnostic, exercised on CPU with gloo in tests/test_sharded_cpu.py); the
 three compute steps are CUDA kernels of libscone_b200 behind the ``ops`` object.
@@ -127,13 +127,16 @@ class ShardedEmbeddingCache:
     ``ops`` supplies match / serve / assemble; the default is :class:`CudaOps` (there is no CPU implementation in the
     product -- tests inject an oracle-backed stand-in to exercise the routing on CPU with gloo).
 
-    The batch is cut into ``micro_batches`` groups of batch rows and software-pipelined: while the packed rows of
-    micro-batch m cross NVLink (all-to-all #2, on the communicator's own stream), the owner-side gather of micro-batch m+1
-    and the requester-side dequantising gather of micro-batch m-1 run on the compute stream.  One stable sort buckets the
-    whole batch by (micro-batch, owner) and one small all-to-all exchanges every bucket size: one host synchronisation.
+    One stable sort buckets the whole batch by (micro-batch, owner) and one small all-to-all exchanges every bucket size:
+    one host synchronisation per batch.  With ``micro_batches > 1`` the batch is cut into groups of batch rows and
+    software-pipelined: while the packed rows of micro-batch m cross NVLink (all-to-all #2, on the communicator's own
+    stream), the owner-side gather of micro-batch m+1 and the requester-side dequantising gather of micro-batch m-1 are
+    enqueued on the compute stream.  MEASURED (config 4 in full, 8 GPUs; profiles/tune_r02.md section 11): 7.88 ms with one
+    micro-batch, 8.16 with four, 8.60 with eight -- the smaller all-to-alls are less efficient and the persistent gather
+    kernels do not leave the communicator the SMs to overlap with; the default is therefore ONE micro-batch.
     """
 
-    def __init__(self, ops, group=None, micro_batches: int = 4):
+    def __init__(self, ops, group=None, micro_batches: int = 1):
         self.ops = ops
         self.group = group
         self.world = dist.get_world_size(group)

@@ -41,7 +41,7 @@ for quant, D, max_n in (("int4", 4096, 5), ("fp16", 1024, 3), ("int8", 2048, 4))
     table = sb.CacheTable(len(mine), D, quant, device=dev)
     table.store(torch.from_numpy(rows[mine]).to(dev))
     base = torch.from_numpy(base_bits.view(np.int16).copy()).view(torch.bfloat16).to(dev)
-    cache = sharded.ShardedEmbeddingCache(sharded.CudaOps(index, table, base))
+    cache = sharded.ShardedEmbeddingCache(sharded.CudaOps(index, table, base), micro_batches=1 if quant == "fp16" else 3)
     emb, fid, ml = cache.lookup(torch.from_numpy(q).to(dev))
     torch.cuda.synchronize()
     got = emb.view(torch.int16).cpu().numpy().view(np.uint16)

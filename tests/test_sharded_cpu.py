@@ -77,7 +77,7 @@ def _worker(rank, world, port, quant, ret):
         assert sharded.shard_rows(N, rank, world) == len(range(rank, N, world))
         local = packed[rank::world]                                 # rows of the ids this rank owns
         q = S.make_stream_numpy(toks, lens, B, L, V, seed=100 + rank)    # each rank has its own batch
-        cache = sharded.ShardedEmbeddingCache(OracleOps(toks, lens, local, (quant, D, soff), base_bits, "bf16"))
+        cache = sharded.ShardedEmbeddingCache(OracleOps(toks, lens, local, (quant, D, soff), base_bits, "bf16"), micro_batches=4)
         emb, fid, ml = cache.lookup(torch.from_numpy(q))
         assert cache.last_plan.micro == 3                              # B = 3 rows: three micro-batches, pipelined
         one = sharded.ShardedEmbeddingCache(cache.ops, micro_batches=1)
