@@ -52,10 +52,9 @@ static int dispatch(int P, EmbedParams &p, int quant, int out_dtype, cudaStream_
     // three-role pipeline of embed_pipe.cuh keeps full-size tiles and wins.  SCONE_EMBED_PIPE=0 / 1 forces one of them
     // (read per call so that the tests can run both everywhere).
     // Measured (config 2 / config 3, us per step, bulk vs pipeline): plain 38.4 / 41.5 and 1004 / 1067; + wpe 51.9 / 47.0 and
-    // 1530 / 1515; + base row 54.2 / 51.4 and 1625 / 1554; both 70.3 / 75.3 and 2383 / 2295.
+    // 1530 / 1515; + base row 54.2 / 51.4 and 1625 / 1554; both 70.3 / 56.3 and 2383 / 2295.
     const char *pe = getenv("SCONE_EMBED_PIPE");
-    const bool extra_pos = p.pos != nullptr, extra_add = p.additive != 0;
-    if (pe ? pe[0] != '0' : ((extra_pos != extra_add) || (extra_pos && extra_add && moved >= 6144))) p.flags |= kEmbedPipe;
+    if (pe ? pe[0] != '0' : (p.pos != nullptr || p.additive != 0)) p.flags |= kEmbedPipe;
     if (p.flags & kEmbedPipe) {
         // full-size tiles on any shape before smaller tiles: the pipeline's matchers do not depend on the row ring
         const int pn[] = {kNarrow6, kMid, kWide, kSmall}, pw[] = {kWide, kSmall};

@@ -777,8 +777,9 @@ static int launch(EmbedParams &p, cudaStream_t stream, int shape) {
                     return launch_pipe<QUANT, OUT, P, 6, 1, 4, 3, ADD>(p, pl, stream);
                 }
                 return kNoFit;
-            case kMid:
-                if (pipe_layout(p, G, 4, 100 * 1024, pl)) return launch_pipe<QUANT, OUT, P, 4, (G >= 2 ? 2 : 1), 8, 2, ADD>(p, pl, stream);
+            case kMid:  // 110 KB x 2 CTAs/SM: two full-size tiles of narrow rows + base row + position row (config 2 "both": 56 us
+                        // against 70 us for the single-ring kernel and 75 us for one 200 KB CTA per SM)
+                if (pipe_layout(p, G, 4, 110 * 1024, pl)) return launch_pipe<QUANT, OUT, P, 4, (G >= 2 ? 2 : 1), 8, 2, ADD>(p, pl, stream);
                 return kNoFit;
             case kWide:
             case kWide3:
