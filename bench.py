@@ -17,7 +17,7 @@ Default (`--workload suite`) prints ONE JSON line (rank 0):
     this box's cores.
   * N = 1 adds `configs`: config 1, config 3 (full size) and config 5 (offloaded tier, as many rows as the box's RAM
     allows), each measured by a child process of this script with its own clocks, hit rate and roofline.
-  * N > 1 adds `sharded`: config 4 -- the table row-sharded over the N GPUs at 12.5 M rows per GPU (819 GB at N = 8) --
+  * N > 1 adds `configs.config3` (N replicas of config 3, the config BASELINE names "on 1 and 8xB200") and `sharded`: config 4 -- the table row-sharded over the N GPUs at 12.5 M rows per GPU (819 GB at N = 8) --
     through the peer-direct fused kernel and through the NCCL all-to-all variant, with NVLink and HBM fractions, a clock
     record, and an in-run bit-exact check of a sample of every rank's output against the oracle.
 
@@ -253,7 +253,7 @@ def _fill_cache(cache, N, D, seed=2, std=0.02, chunk_bytes=1 << 30):
         cache.cache_embeddings(range(s, s + k), rows, verbose=False)
 
 
-def run_ours(args, w, rank, local_rank, world, name):
+def run_ours(args, w, rank, local_rank, world, name, steps=None):
     """Returns the JSON line (a dict) on rank 0, None elsewhere.  Leaves the process group alive."""
     import numpy as np
     import torch
@@ -284,7 +284,7 @@ def run_ours(args, w, rank, local_rank, world, name):
 
     B, L, D, N, V = w["B"], w["L"], w["D"], w["N"], w["V"]
     T = B * L
-    steps = args.steps
+    steps = steps or args.steps
     # ---- build (untimed): the drop-in objects -- extractor (vocabulary + device index), cache (table), fallback rows ----
     toks, lens, longest = S.make_vocab_device(N, w["max_n"], V, seed=0, device=dev, return_longest=True)
     ex = sb.NGramExtractor.from_arrays(toks.cpu().numpy(), lens.cpu().numpy(), device=dev)
@@ -964,6 +964,20 @@ def run_suite(args, rank, local_rank, world):
                 print(json.dumps(line), flush=True)
             os._exit(0)
 
+    if not args.no_configs:
+        # config 3 is named "on 1 and 8xB200": its 21 GB table fits every GPU, so at N > 1 it is N replicas with their own batches
+        t0 = time.perf_counter()
+        try:
+            c3 = run_ours(args, WORKLOADS["config3"], rank, local_rank, world, "config3", steps=max(3, min(args.steps, 20))) or {}
+            c3 = {k: c3.get(k) for k in ("value", "unit", "ms_per_step", "steps", "dtype", "gpu_launches", "clocks", "roofline", "e2e", "parity",
+                                         "config") if c3.get(k) is not None}
+        except Exception as e:
+            c3 = {"error": repr(e)}
+        c3["wall_seconds"] = time.perf_counter() - t0
+        if rank == 0:
+            line["configs"] = {"config3": c3}
+        import gc
+        gc.collect()
     if not args.no_sharded:
         threading.Thread(target=watchdog, daemon=True).start()
         torch.cuda.empty_cache()
