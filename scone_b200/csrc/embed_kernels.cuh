@@ -741,7 +741,7 @@ static int launch(EmbedParams &p, cudaStream_t stream, int shape) {
     constexpr int G = 32 / P;
     BulkLayout lay;
 #ifdef SCONE_TUNE
-    if constexpr (OUT == SCONE_OUT_BF16 && (P == 4 || P == 8) && (QUANT == SCONE_QUANT_INT8 || QUANT == SCONE_QUANT_INT4)) {
+    if constexpr (OUT == SCONE_OUT_BF16 && (P == 4 || P == 8)) {
         const Variant v = variant();
 #define SCONE_B(NMM, NGG, MM)                                                                                               \
     if (v.kind == 1 && v.nm == NMM && v.ng == NGG && v.minb == MM && bulk_layout(p, G, NMM, v.smem_kb * 1024, lay)) \

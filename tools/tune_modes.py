@@ -27,7 +27,11 @@ def main():
         from scone_b200 import _lib
         _lib.LIB_PATH = os.path.abspath(os.environ["AB_LIB"])
     name = sys.argv[1]
-    w = bench.WORKLOADS[name]
+    if name.startswith("custom:"):      # custom:D:quant:max_n:N:B:L:V (as tools/tune_embed.py)
+        _, D_, q_, mn_, N_, B_, L_, V_ = name.split(":")
+        w = dict(N=int(N_), D=int(D_), V=int(V_), max_n=int(mn_), quant=q_, B=int(B_), L=int(L_), desc=name)
+    else:
+        w = bench.WORKLOADS[name]
     dev = torch.device("cuda", 0)
     B, L, D, N, V = w["B"], w["L"], w["D"], w["N"], w["V"]
     T = B * L
