@@ -676,6 +676,7 @@ template <int QUANT, int OUT, int P, int NM, int NG, int MINB, bool ADD>
 static int launch_bulk(EmbedParams &p, const BulkLayout &lay, cudaStream_t stream) {
     constexpr int G = 32 / P;
     auto kern = embed_bulk_kernel<QUANT, OUT, P, NM, NG, MINB, ADD>;
+    if (p.stagger_ns < 0) p.stagger_ns = 0;  // "off" from a SCONE_TUNE override on a shape that does not stagger
     static int configured[64] = {0};  // per device: the attribute lives in the device's context
     int dev = 0;
     SCONE_CUDA(cudaGetDevice(&dev));
@@ -694,6 +695,7 @@ static int launch_pipe(EmbedParams &p, const PipeLayout &lay, cudaStream_t strea
     constexpr int G = 32 / P;
     static_assert(NL <= G, "a loader without a position");
     auto kern = embed_pipe_kernel<QUANT, OUT, P, NM, NL, NG, MINB, ADD>;
+    if (p.stagger_ns < 0) p.stagger_ns = 0;  // "off" from a SCONE_TUNE override on a shape that does not stagger
     static int configured[64] = {0};  // per device: the attribute lives in the device's context
     int dev = 0;
     SCONE_CUDA(cudaGetDevice(&dev));
@@ -771,10 +773,15 @@ static int launch(EmbedParams &p, cudaStream_t stream, int shape) {
         PipeLayout pl;
         switch (shape) {
             case kNarrow6:
-            case kNarrow4:
                 if (pipe_layout(p, G, 6, 70 * 1024, pl)) {
                     set_stagger<P, 6, 3>(p);
                     return launch_pipe<QUANT, OUT, P, 6, 1, 4, 3, ADD>(p, pl, stream);
+                }
+                return kNoFit;
+            case kNarrow4:  // two loaders: rows of 3-4 KB without extra rows (fp32 rows at D 768 / 1024)
+                if (pipe_layout(p, G, 5, 70 * 1024, pl)) {
+                    set_stagger<P, 5, 3>(p);
+                    return launch_pipe<QUANT, OUT, P, 5, (G >= 2 ? 2 : 1), 4, 3, ADD>(p, pl, stream);
                 }
                 return kNoFit;
             case kMid:  // 110 KB x 2 CTAs/SM: two full-size tiles of narrow rows + base row + position row (config 2 "both": 56 us
