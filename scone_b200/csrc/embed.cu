@@ -53,17 +53,19 @@ static int dispatch(int P, EmbedParams &p, int quant, int out_dtype, cudaStream_
     // (read per call so that the tests can run both everywhere).
     // Measured (config 2 / config 3, us per step, bulk vs pipeline): plain 38.4 / 41.5 and 1004 / 1067; + wpe 51.9 / 47.0 and
     // 1530 / 1515; + base row 54.2 / 51.4 and 1625 / 1554; both 70.3 / 56.3 and 2383 / 2295.
-    // Plain path with rows of 2-4 KB (the reference's own fp32 rows at D 768 / 1024): the single ring only holds two full-size
-    // tiles, its matchers starve, and the pipeline wins as well (43.4 vs 46.2 us and 59.0 vs 63.7 us, tune_r02.md section 14).
+    // Plain path with fp32 rows of 2-6 KB (the reference's own row format at D 768 .. 1536): a position moves twice as many
+    // bytes in as out, the single ring holds two tiles or fewer for its matchers, and the pipeline wins as well (us per step at
+    // D 768 / 1024 / 1280 / 1536: 52.9 -> 48.2, 66.4 -> 61.1, 92.2 -> 76.8, 102.2 -> 90.9; FP16 / INT8 / INT4 rows of any width
+    // and fp32 rows of 8 KB stay 1-4 % faster on the single ring: profiles/tune_r02.md section 17).
     const char *pe = getenv("SCONE_EMBED_PIPE");
     const bool extra_rows = p.pos != nullptr || p.additive != 0;
-    const int64_t slot = p.row_stride > 2ll * p.D ? p.row_stride : 2ll * p.D;
-    if (pe ? pe[0] != '0' : (extra_rows || (slot > 2048 && slot <= 4096))) p.flags |= kEmbedPipe;
+    const bool heavy_rows = p.row_stride > 2ll * p.D && p.row_stride > 2048 && p.row_stride <= 6144;
+    if (pe ? pe[0] != '0' : (extra_rows || heavy_rows)) p.flags |= kEmbedPipe;
     if (p.flags & kEmbedPipe) {
         // full-size tiles on any shape before smaller tiles: the pipeline's matchers do not depend on the row ring
         const int plain[] = {kNarrow4, kNarrow6, kMid, kWide, kSmall}, pn[] = {kNarrow6, kMid, kWide, kSmall}, pw[] = {kMid, kWide, kSmall};
-        const int *po = !extra_rows && slot <= 4096 ? plain : moved >= 6144 ? pw : pn;
-        const int n_po = !extra_rows && slot <= 4096 ? 5 : moved >= 6144 ? 3 : 4;
+        const int *po = !extra_rows ? plain : moved >= 6144 ? pw : pn;
+        const int n_po = !extra_rows ? 5 : moved >= 6144 ? 3 : 4;
         for (int pp = P; pp <= 8 && rc == kNoFit; pp <<= 1)
             for (int s = 0; s < n_po && rc == kNoFit; ++s) rc = dispatch_one(pp, p, quant, out_dtype, stream, po[s]);
     }

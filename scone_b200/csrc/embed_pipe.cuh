@@ -13,10 +13,12 @@
 //     storage, so tiles stay at the full G = 32 / P positions whatever a position's rows weigh, and the probe chains of
 //     many tiles are in flight;
 //   * NL loader warps walk the CTA's tiles in order, wait for a free row slot and issue the bulk copies (position g of a tile
-//     is staged by loader g % NL: table or fallback row [+ base row of a hit] [+ position row]).  Every loader takes part in
+//     is staged by loader g % NL: table or fallback row [+ base row of a hit]).  Every loader takes part in
 //     every tile, so the row ring only needs two slots and no slot-ownership rule.  Why several: a cp.async.bulk costs
 //     ~80 ns to issue and the issues of one warp serialise -- with three rows per position ONE loader spent 1.9 us per
-//     tile of 8 positions and capped config 2 + base row + wpe at 104 us (profiles/tune_r02.md);
+//     tile of 8 positions and capped config 2 + base row + wpe at 104 us (profiles/tune_r02.md).  For the same reason the
+//     position rows of a tile are ONE copy: its G positions are consecutive in their sequence, so their wpe rows are one
+//     contiguous block of G x 2 D bytes (two blocks where the tile straddles the end of a sequence);
 //   * gather warps are those of embed_bulk_kernel; the one that owns a tile's first position also writes the tile's
 //     fgram_id / match_len (from the slot header), so matchers and loader never write global memory: with
 //     SCONE_EMBED_INPUTS_STABLE they run under the previous kernel's tail without ever waiting for it.
@@ -29,8 +31,10 @@ constexpr int kMaxMetaRing = 32;
 struct PipeLayout {
     int ring;        // row-ring slots (tiles staged or being consumed)
     int meta_ring;   // metadata-ring slots, a multiple of NM
-    int slot_bytes;  // bytes reserved per position (see BulkLayout)
-    int pos_off, add_off;
+    int slot_bytes;  // bytes reserved per position: table / fallback row [+ base row of a hit at add_off]
+    int add_off;
+    int pos_off;     // offset of the tile's block of G position rows (2 D bytes each, contiguous) from the tile's first slot, or 0
+    int tile_bytes;  // G slots + the position block
     int smem_bytes;
 };
 
@@ -143,7 +147,7 @@ __global__ void __launch_bounds__(32 * (NM + NL + NG), MINB) embed_pipe_kernel(c
             if (lane == 0) mbar_arrive(&meta_empty[ms]);  // the entries are in registers: the matcher may reuse the slot
             const int64_t i = tile * G + lane;
             const bool owner = lane < G && (lane % NL) == ld && i < p.T;
-            const uint8_t *src = nullptr, *src2 = nullptr, *src3 = nullptr;
+            const uint8_t *src = nullptr, *src3 = nullptr;
             uint32_t bytes = 0;
             if (owner) {
                 if (e.x >= 0) {
@@ -154,9 +158,11 @@ __global__ void __launch_bounds__(32 * (NM + NL + NG), MINB) embed_pipe_kernel(c
                     src = p.base + (int64_t)e.y * p.D * 2;
                     bytes = (uint32_t)p.D * 2u;
                 }
-                if (lay.pos_off) src2 = p.pos + pos_in_row(i, p.L, p.T) * p.D * 2;    // fused position add
             }
-            uint32_t total = bytes + (src2 ? (uint32_t)p.D * 2u : 0u) + (src3 ? (uint32_t)p.D * 2u : 0u);
+            // fused position add: the tile's position rows, staged as one block by an otherwise idle lane of the last loader
+            const int64_t i0 = tile * G;
+            const int npos = (lay.pos_off && ld == NL - 1 && lane == 31) ? (int)(p.T - i0 < G ? p.T - i0 : G) : 0;
+            uint32_t total = bytes + (src3 ? (uint32_t)p.D * 2u : 0u) + (uint32_t)npos * (uint32_t)p.D * 2u;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xFFFFFFFFu, total, o);
             mbar_wait(&empty_bar[q], (uint32_t)(((itl / R) & 1) ^ 1));
@@ -174,10 +180,20 @@ __global__ void __launch_bounds__(32 * (NM + NL + NG), MINB) embed_pipe_kernel(c
             }
             if (lane == 0) mbar_arrive_expect_tx(&full_bar[q], total);
             __syncwarp();
-            uint8_t *slot = rows_smem + (size_t)(q * G + lane) * lay.slot_bytes;
+            uint8_t *tile_smem = rows_smem + (size_t)q * lay.tile_bytes;
+            uint8_t *slot = tile_smem + (size_t)lane * lay.slot_bytes;
             if (bytes) bulk_g2s(slot, src, bytes, &full_bar[q], e.x >= 0 ? pol : pol_base);
-            if (src2) bulk_g2s(slot + lay.pos_off, src2, (uint32_t)p.D * 2u, &full_bar[q], pol_keep);
             if (src3) bulk_g2s(slot + add_off, src3, (uint32_t)p.D * 2u, &full_bar[q], pol_base);
+            if (npos) {
+                int64_t cur = pos_in_row(i0, p.L, p.T);
+                for (int j = 0; j < npos;) {  // one pass unless the tile crosses the end of a sequence
+                    const int seg = (int)(p.L - cur < npos - j ? p.L - cur : npos - j);
+                    bulk_g2s(tile_smem + lay.pos_off + (size_t)j * p.D * 2, p.pos + cur * p.D * 2, (uint32_t)seg * (uint32_t)p.D * 2u, &full_bar[q],
+                             pol_keep);
+                    j += seg;
+                    cur = 0;
+                }
+            }
         }
     } else {
         // ===== gather warps: every warp waits for and releases every tile, in order =====
@@ -201,10 +217,11 @@ __global__ void __launch_bounds__(32 * (NM + NL + NG), MINB) embed_pipe_kernel(c
                 const int2 e = hdr[q * G + j];
                 const int64_t t = tile * G + j;
                 if (t < p.T) {
-                    const uint8_t *slot = rows_smem + (size_t)(q * G + j) * lay.slot_bytes;
+                    const uint8_t *tile_smem = rows_smem + (size_t)q * lay.tile_bytes;
+                    const uint8_t *slot = tile_smem + (size_t)j * lay.slot_bytes;
                     const uint8_t *arow = (add_off && e.x >= 0 && e.y >= 0) ? slot + add_off : nullptr;
-                    stream_from_smem<QUANT, OUT>(p, slot, arow, lay.pos_off ? slot + lay.pos_off : nullptr, e.x, e.y, p.out + t * p.D * 2, lane,
-                                                 pol);
+                    stream_from_smem<QUANT, OUT>(p, slot, arow, lay.pos_off ? tile_smem + lay.pos_off + (size_t)j * p.D * 2 : nullptr, e.x, e.y,
+                                                 p.out + t * p.D * 2, lane, pol);
                     flagged |= e.y < 0 && (e.x < 0 || add_off);
                 }
             }
@@ -224,11 +241,12 @@ static bool pipe_layout(const EmbedParams &p, int G, int nm, int budget_bytes, P
         lay.add_off = (int)slot;
         slot += (2ll * p.D + 127) / 128 * 128;
     }
+    int64_t per_tile = slot * G;
     if (p.pos) {
-        lay.pos_off = (int)slot;
-        slot += (2ll * p.D + 127) / 128 * 128;
+        lay.pos_off = (int)per_tile;
+        per_tile += (2ll * p.D * G + 127) / 128 * 128;
     }
-    const int64_t per_tile = slot * G;
+    if (per_tile > (1 << 20) - 16) return false;  // an mbarrier phase counts at most 2^20 - 1 bytes
     int ring = (int)((budget_bytes - pipe_header_bytes(G)) / per_tile);
     if (ring > kMaxRing) ring = kMaxRing;
     if (ring < 2) return false;
@@ -236,6 +254,7 @@ static bool pipe_layout(const EmbedParams &p, int G, int nm, int budget_bytes, P
     lay.meta_ring = kMaxMetaRing / nm * nm;  // a multiple of NM: a metadata slot is only ever filled by one matcher
     if (lay.meta_ring > 4 * nm) lay.meta_ring = 4 * nm;
     lay.slot_bytes = (int)slot;
+    lay.tile_bytes = (int)per_tile;
     lay.smem_bytes = pipe_header_bytes(G) + (int)(per_tile * ring);
     return true;
 }

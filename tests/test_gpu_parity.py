@@ -318,8 +318,10 @@ def test_embed_forward_status_and_fallback_edges():
 def test_embed_forward_with_positions():
     """Fused wpe add (language_model.py:253-254): fp32(row) + fp32(pos), one RNE rounding."""
     sb, S = _mods()
-    for quant, out_dtype in (("int8", "bf16"), ("fp16", "fp16"), ("int4", "bf16")):
-        N, D, V, max_n, B, L = 1000, 256, 300, 4, 4, 97
+    # L = 97: tiles straddle the end of a sequence; L = 3 / 1: a tile spans several sequences (its position rows are several blocks)
+    for quant, out_dtype, B, L in (("int8", "bf16", 4, 97), ("fp16", "fp16", 4, 97), ("int4", "bf16", 4, 97), ("int8", "bf16", 41, 3),
+                                   ("fp32", "bf16", 37, 1)):
+        N, D, V, max_n = 1000, 256, 300, 4
         toks, lens = S.make_vocab_numpy(N, max_n, V, seed=21)
         q = S.make_stream_numpy(toks, lens, B, L, V, seed=22, p_plant=0.7)
         rows = S.make_rows_numpy(N, D, seed=23)
