@@ -319,10 +319,11 @@ def test_embed_forward_with_positions():
     """Fused wpe add (language_model.py:253-254): fp32(row) + fp32(pos), one RNE rounding."""
     sb, S = _mods()
     # L = 97: tiles straddle the end of a sequence; L = 3 / 1: a tile spans several sequences (its position rows are several blocks)
-    for quant, out_dtype, B, L in (("int8", "bf16", 4, 97), ("fp16", "fp16", 4, 97), ("int4", "bf16", 4, 97), ("int8", "bf16", 41, 3),
-                                   ("fp32", "bf16", 37, 1)):
-        N, D, V, max_n = 1000, 256, 300, 4
-        toks, lens = S.make_vocab_numpy(N, max_n, V, seed=21)
+    # max_n = 1 / 2: 32 / 16 positions per tile (with 32 the lane that stages the position block also stages a row)
+    for quant, out_dtype, B, L, max_n in (("int8", "bf16", 4, 97, 4), ("fp16", "fp16", 4, 97, 4), ("int4", "bf16", 4, 97, 4), ("int8", "bf16", 41, 3, 4),
+                                          ("fp32", "bf16", 37, 1, 4), ("fp16", "bf16", 9, 50, 1), ("int8", "fp16", 7, 45, 2), ("fp32", "bf16", 30, 5, 1)):
+        N, D, V = (1000, 256, 300) if max_n > 1 else (60, 256, 300)
+        toks, lens = S.make_vocab_numpy(N, max_n, V, seed=21, min_n=min(2, max_n))
         q = S.make_stream_numpy(toks, lens, B, L, V, seed=22, p_plant=0.7)
         rows = S.make_rows_numpy(N, D, seed=23)
         base_bits = po.cast_bits(S.make_rows_numpy(V, D, seed=24), out_dtype)
@@ -986,7 +987,7 @@ def test_sharded_tier_two_gpus_reference_api(tmp_path):
 
 
 @pytest.mark.parametrize("Hf,H,k", [(384, 768, 1000), (768, 1024, 517), (96, 256, 300), (1024, 4096, 260), (8, 64, 1), (72, 320, 129),
-                                    (40, 448, 257)])
+                                    (40, 448, 257), (64, 2048, 9000), (48, 1280, 7000), (32, 512, 40000)])
 def test_projection_fold(Hf, H, k):
     """table[row] = quantise(rows @ W^T): the reference's bias-free f_gram_projection (language_model.py:172-176, :236) folded
     into the table build by a tcgen05 / TMEM GEMM whose epilogue is the quantiser.
@@ -1008,11 +1009,20 @@ def test_projection_fold(Hf, H, k):
     x_src = x[perm]                                 # row r of the input went to table row perm[r]
     assert np.all(np.abs(x_src - P) <= bound + 1e-30), float(np.max(np.abs(x_src - P) - bound))
     assert np.array_equal(x_src[min(3, k - 1)], np.zeros(H, np.float32))
-    for quant in ("fp16", "int8", "int4"):
+    import os
+    # INT8 twice: row absmax exchanged between the CTAs of a cluster (one sweep; the default for 256 < H <= 2048; the large-k
+    # shapes give every cluster several row tiles) and the two-sweep path
+    for quant in ("fp16", "int8", "int8-two-sweeps", "int4"):
         if quant == "int4" and H % 128:
             continue                                # INT4 groups of 128 columns
+        if quant == "int8-two-sweeps":
+            quant = "int8"
+            os.environ["SCONE_FOLD_XCH"] = "0"
         tq = sb.CacheTable(k, H, quant)
-        tq.store_projected(torch.from_numpy(rows).to(DEV), torch.from_numpy(W).to(DEV), row_ids=torch.from_numpy(perm).to(DEV))
+        try:
+            tq.store_projected(torch.from_numpy(rows).to(DEV), torch.from_numpy(W).to(DEV), row_ids=torch.from_numpy(perm).to(DEV))
+        finally:
+            os.environ.pop("SCONE_FOLD_XCH", None)
         ref = sb.CacheTable(k, H, quant)
         ref.store(torch.from_numpy(x).to(DEV))
         assert torch.equal(tq.storage, ref.storage), quant

@@ -17,8 +17,9 @@ dev = torch.device("cuda", 0)
 peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
 peak = float(peaks.get("bf16_tflops", 1590.0))
 hbm = float(peaks.get("hbm_gbs", 6650.0))
-for Hf, H, quant in ((384, 768, "fp16"), (384, 1024, "int8"), (768, 1024, "int8"), (768, 1024, "fp16"), (1024, 4096, "int4"), (1024, 4096, "fp16"),
-                     (1024, 4096, "fp32")):
+two_sweeps = os.environ.get("SCONE_FOLD_XCH") == "0"
+for Hf, H, quant in ((384, 768, "fp16"), (384, 1024, "int8"), (768, 1024, "int8"), (768, 1024, "fp16"), (1024, 2048, "int8"), (1024, 4096, "int4"),
+                     (1024, 4096, "fp16"), (1024, 4096, "fp32")):
     kk = min(k, (8 << 30) // (4 * H))
     rows = torch.randn((kk, Hf), device=dev, dtype=torch.bfloat16)
     W = torch.randn((H, Hf), device=dev, dtype=torch.bfloat16) * Hf ** -0.5
@@ -34,7 +35,7 @@ for Hf, H, quant in ((384, 768, "fp16"), (384, 1024, "int8"), (768, 1024, "int8"
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
-    sweeps = 2 if (quant == "int8" and H > 256) else 1
+    sweeps = 2 if (quant == "int8" and H > 256 and (two_sweeps or H > 2048)) else 1
     flops = 2.0 * kk * Hf * H
     byts = kk * Hf * 2 + kk * t.row_stride
     # what cuBLAS + the separate quantise pass would cost: the library GEMM alone, for reference
@@ -47,7 +48,7 @@ for Hf, H, quant in ((384, 768, "fp16"), (384, 1024, "int8"), (768, 1024, "int8"
     e1.record()
     torch.cuda.synchronize()
     ms_lib = e0.elapsed_time(e1) / reps
-    print(json.dumps({"H_f": Hf, "H": H, "quant": quant, "rows": kk, "ms": ms, "TFLOPs_useful": flops / ms / 1e9, "frac_of_bf16_peak": flops / ms / 1e9 / peak,
+    print(json.dumps({"H_f": Hf, "H": H, "quant": quant, "sweeps": sweeps, "rows": kk, "ms": ms, "TFLOPs_useful": flops / ms / 1e9, "frac_of_bf16_peak": flops / ms / 1e9 / peak,
                       "TFLOPs_issued": sweeps * flops / ms / 1e9, "GBs": byts / ms / 1e6, "frac_of_hbm_peak": byts / ms / 1e6 / hbm,
                       "cublas_bf16_gemm_only_ms": ms_lib, "peak_tflops": peak}), flush=True)
     del rows, W, t, c
