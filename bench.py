@@ -709,8 +709,6 @@ def run_sharded(args, w, rank, local_rank, world, modes=("peer", "nccl"), parity
                          "frac": bpt * T / step_s / 1e9 / peak, "traffic": None, "peak_source": peak_src, "bytes_per_token": bpt,
                          "note": "HBM bytes per GPU against the HBM peak; the binding resource at W > 1 is NVLink, see nvlink.frac"},
         }
-        if mode == "nccl":
-            result[mode]["nccl_env"] = {k: os.environ.get(k) for k in NCCL_ENV}
     assert int(status.item()) == 0
     # ---- in-run parity: rows 0-1 of every rank's batch 0 against the oracle ------------------------------------------
     if parity:
@@ -998,16 +996,7 @@ def run_suite(args, rank, local_rank, world):
         pass
 
 
-# NCCL point-to-point channels for the all-to-all variant of the sharded tier: the default channel count limits
-# all_to_all_single to ~430 GB/s between two B200s; 64 channels measured 7.23 -> 5.99 ms per step at 2 GPUs
-# (profiles/tune_r02.md section 20).  Set before the communicator exists; anything the caller exported wins.
-NCCL_ENV = {"NCCL_MIN_P2P_NCHANNELS": "64", "NCCL_MAX_P2P_NCHANNELS": "64", "NCCL_MAX_NCHANNELS": "64"}
-
-
 def main():
-    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and os.environ.get("SCONE_BENCH_NCCL_ENV", "1") != "0":
-        for k, v in NCCL_ENV.items():
-            os.environ.setdefault(k, v)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
