@@ -709,17 +709,23 @@ static int launch_pipe(EmbedParams &p, const PipeLayout &lay, cudaStream_t strea
     return launch_pdl(kern, blocks, 32 * (NM + NL + NG), (size_t)lay.smem_bytes, stream, p, lay);
 }
 
-// Kernel selection (measured on B200, profiles/tune_r01.md).  Rows that fit a shared-memory ring go through the
-// bulk-copy variant; its shape follows the traffic per position:
+// Kernel selection (measured on B200, profiles/tune_r01.md and tune_r02.md).  Rows that fit a shared-memory ring go through
+// one of the two bulk-copy kernels (embed.cu picks: single ring for the plain path, pipeline for extra rows per position and
+// for fp32 rows of 2-6 KB); the shape follows the traffic per position.  Single-ring kernel (embed_bulk_kernel):
 //   kNarrow6  < 6 KB moved, tiny rows : 6 matcher + 4 gather warps, 3 CTAs/SM, 70 KB ring  (needs >= 6 ring slots)
 //   kNarrow4  < 6 KB moved            : 4 matcher + 4 gather warps, 3 CTAs/SM, 70 KB ring  -- matcher-hungry
 //   kWide    >= 6 KB moved            : 6 matcher + 12 gather warps, 1 CTA/SM, 200 KB ring -- store-hungry
 //   kWide3   wide rows + position row : 3 matcher + 12 gather warps, 1 CTA/SM, 200 KB ring (when six slots do not fit)
 //   kWide2   wide rows + base + pos row: 2 matcher + 12 gather warps, 1 CTA/SM, 200 KB ring (two slots are enough)
-//   kMid     narrow rows + extra rows : 4 matcher + 8 gather warps, 2 CTAs/SM, 100 KB ring (config 2 with base row AND
-//                                       position row staged: 76-80 us against 92-95 us for kSmall)
+//   kMid     narrow rows + extra rows : 4 matcher + 8 gather warps, 2 CTAs/SM, 100 KB ring
 //   kSmall   anything                 : 2 matcher + 6 gather warps, 3 CTAs/SM, 70 KB ring
 //   kLdg     rows too wide for a ring : register-load variant
+// Pipeline kernel (embed_pipe_kernel; the ring only needs two full-size tiles), matcher + loader + gather warps:
+//   kNarrow6  6 + 1 + 4, 3 CTAs/SM, 70 KB    (config 2 + wpe: 47 us; + base row: 51 us)
+//   kNarrow4  5 + 2 + 4, 3 CTAs/SM, 70 KB    (plain path, fp32 rows of 3-4 KB)
+//   kMid      4 + 2 + 8, 2 CTAs/SM, 110 KB   (config 2 + base row + wpe: 56 us; fp32 rows of 5-6 KB)
+//   kWide*    6 + 4 + 12, 1 CTA/SM, 200 KB   (config 3 modes)
+//   kSmall    2 + 1 + 6, 3 CTAs/SM, 70 KB
 // A shape that does not fit with P lanes per position is retried with 2P, 4P (fewer positions per tile = smaller ring
 // slots) before the next shape is considered.
 enum Shape : int { kNarrow6 = 0, kNarrow4 = 1, kWide = 2, kSmall = 3, kLdg = 4, kWide3 = 5, kMid = 6, kWide2 = 7 };

@@ -61,6 +61,18 @@ for quant, D, max_n in (("int4", 4096, 5), ("fp16", 1024, 3), ("int8", 2048, 4))
         and int(status.item()) == 0
     print(f"rank {rank}/{world} {quant} D={D} peer-direct: {'OK' if good2 else 'MISMATCH'}", flush=True)
     ok = ok and good2
+    # the same with the fused position add: the pipeline kernel pulls the rows from the peers and stages the position rows
+    pos_bits = po.cast_bits(S.make_rows_numpy(L, D, seed=7), "bf16")
+    want_p, _, _, _ = COracleIndex(toks, lens).embed(quant, D, 128, packed, stride, packed[:, soff:] if soff else None, stride, base_bits, q,
+                                                     "bf16", nthreads=4, pos_bits=pos_bits)
+    pos = torch.from_numpy(pos_bits.view(np.int16).copy()).view(torch.bfloat16).to(dev)
+    emb2p, fid2p, _ = sharded.embed_forward_sharded(index, pt, base, torch.from_numpy(q).to(dev), pos_emb=pos, status=status)
+    torch.cuda.synchronize()
+    dist.barrier()
+    good2p = np.array_equal(emb2p.view(torch.int16).cpu().numpy().view(np.uint16), want_p) and np.array_equal(fid2p.cpu().numpy(), wid) \
+        and int(status.item()) == 0
+    print(f"rank {rank}/{world} {quant} D={D} peer-direct + wpe: {'OK' if good2p else 'MISMATCH'}", flush=True)
+    ok = ok and good2p
 # the drop-in class with tier="sharded": every rank offers all rows, keeps its own, looks up through peer memory
 ex = sb.NGramExtractor.from_arrays(toks, lens)
 cache = sb.EmbeddingCache(ex, D, quant=quant, out_dtype=torch.bfloat16, device=dev, tier="sharded")
