@@ -338,3 +338,64 @@ def test_compact20_slot_packing_is_injective():
         key = (w[0] >> 28, w[1], w[2], w[3])
         assert seen.setdefault(key, toks) == toks                 # equal key words <=> equal (length, tokens)
     assert pack(2 ** 28 - 2, [PAD - 1] * 5)[0] != 0xFFFFFFFF
+
+
+def test_fold_reciprocal_division_is_the_correctly_rounded_quotient():
+    """csrc/fold.cu divides by a per-row scale as: refined reciprocal once (rcp seed, one Newton step), then per element
+    q = a*y; r = fma(-b, q, a); q = fma(r, y, q); r = fma(-b, q, a); q = fma(r, y, q) -- and claims the result IS the IEEE quotient
+    (the oracle's `x / s`).  Checked here in exact rational arithmetic (every fma rounded once, to nearest even, 24-bit
+    significand), for reciprocal seeds up to 2 ulp off (the hardware's rcp.approx is within 1), on random operands and on the
+    adversarial ones: quotients at and next to the .5 ties that `rint` would flip."""
+    from fractions import Fraction as F
+    import random
+
+    def rn32(x):                                    # exact rational -> nearest binary32 (as a Fraction); normal range only
+        if x == 0:
+            return F(0)
+        s, a = (1, x) if x > 0 else (-1, -x)
+        e = a.numerator.bit_length() - a.denominator.bit_length()
+        if F(2) ** e > a:
+            e -= 1
+        assert F(2) ** e <= a < F(2) ** (e + 1) and -100 < e < 100
+        ulp = F(2) ** (e - 23)
+        n, rem = divmod(a, ulp)
+        if rem * 2 > ulp or (rem * 2 == ulp and n % 2 == 1):
+            n += 1
+        return s * n * ulp
+
+    def ulp_of(x):
+        e = x.numerator.bit_length() - x.denominator.bit_length()
+        if F(2) ** e > abs(x):
+            e -= 1
+        return F(2) ** (e - 23)
+
+    def fold_div(a, b, seed_off):
+        y0 = rn32(1 / b)
+        y0 += seed_off * ulp_of(y0)
+        e = rn32(1 - b * y0)
+        y = rn32(y0 + y0 * e)
+        q = rn32(a * y)
+        r = rn32(a - b * q)
+        q = rn32(q + r * y)
+        r = rn32(a - b * q)
+        return rn32(q + r * y)
+
+    rng = random.Random(7)
+    cases = []
+    for _ in range(800):
+        amax = rn32(F(rng.getrandbits(24) | (1 << 23)) * F(2) ** rng.randint(-60, 20))
+        b = rn32(amax / 127)                        # the INT8 row scale; the INT4 group scale amax / 7 below
+        if rng.random() < 0.3:
+            b = rn32(amax / 7)
+        for _ in range(6):
+            cases.append((rn32(amax * F(rng.randint(-(1 << 24), 1 << 24), 1 << 24)), b))      # anywhere in [-amax, amax]
+            k = rng.randint(-127, 126)
+            tie = rn32((F(k) + F(1, 2)) * b)                                                    # a / b next to k + 0.5
+            cases.append((tie, b))
+            cases.append((tie + rng.choice((-1, 1)) * ulp_of(tie), b))
+    bad = 0
+    for a, b in cases:
+        want = rn32(a / b)
+        for off in (-2, -1, 0, 1, 2):
+            bad += fold_div(a, b, off) != want
+    assert bad == 0, f"{bad} of {5 * len(cases)} quotients are not correctly rounded"
