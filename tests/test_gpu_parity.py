@@ -1003,26 +1003,39 @@ def test_projection_fold(Hf, H, k):
     rows[min(3, k - 1)] = 0.0                       # an all-zero row: scale 1
     P, bound = po.fold_projection(rows, W)
     perm = rng.permutation(k)
-    t32 = sb.CacheTable(k, H, "fp32")
-    t32.store_projected(torch.from_numpy(rows).to(DEV), torch.from_numpy(W).to(DEV), row_ids=torch.from_numpy(perm).to(DEV))
-    x = t32.gather(torch.arange(k, device=DEV)).cpu().numpy()
-    x_src = x[perm]                                 # row r of the input went to table row perm[r]
-    assert np.all(np.abs(x_src - P) <= bound + 1e-30), float(np.max(np.abs(x_src - P) - bound))
-    assert np.array_equal(x_src[min(3, k - 1)], np.zeros(H, np.float32))
     import os
+    # both tensor-core paths: CTA pairs on one 256 x 256 tile (tcgen05.mma.cta_group::2; the default for FP32 / FP16 tables with
+    # K >= 512) and one 128 x 256 tile per CTA
+    xs = {}
+    for two_sm in ("0", "1"):
+        os.environ["SCONE_FOLD_2SM"] = two_sm
+        try:
+            t32 = sb.CacheTable(k, H, "fp32")
+            t32.store_projected(torch.from_numpy(rows).to(DEV), torch.from_numpy(W).to(DEV), row_ids=torch.from_numpy(perm).to(DEV))
+        finally:
+            os.environ.pop("SCONE_FOLD_2SM", None)
+        x = t32.gather(torch.arange(k, device=DEV)).cpu().numpy()
+        xs[two_sm] = x
+        x_src = x[perm]                             # row r of the input went to table row perm[r]
+        assert np.all(np.abs(x_src - P) <= bound + 1e-30), (two_sm, float(np.max(np.abs(x_src - P) - bound)))
+        assert np.array_equal(x_src[min(3, k - 1)], np.zeros(H, np.float32))
     # INT8 twice: row absmax exchanged between the CTAs of a cluster (one sweep; the default for 256 < H <= 2048; the large-k
     # shapes give every cluster several row tiles) and the two-sweep path
-    for quant in ("fp16", "int8", "int8-two-sweeps", "int4"):
-        if quant == "int4" and H % 128:
+    for quant in ("fp16", "fp16-pair-tile", "int8", "int8-two-sweeps", "int8-two-sweeps-pair-tile", "int4", "int4-pair-tile"):
+        if quant.startswith("int4") and H % 128:
             continue                                # INT4 groups of 128 columns
-        if quant == "int8-two-sweeps":
-            quant = "int8"
+        if "two-sweeps" in quant:
             os.environ["SCONE_FOLD_XCH"] = "0"
+        two_sm = "1" if quant.endswith("pair-tile") else "0"
+        os.environ["SCONE_FOLD_2SM"] = two_sm
+        x = xs[two_sm]                              # the fp32 product of the same tensor-core path
+        quant = quant.split("-")[0]
         tq = sb.CacheTable(k, H, quant)
         try:
             tq.store_projected(torch.from_numpy(rows).to(DEV), torch.from_numpy(W).to(DEV), row_ids=torch.from_numpy(perm).to(DEV))
         finally:
             os.environ.pop("SCONE_FOLD_XCH", None)
+            os.environ.pop("SCONE_FOLD_2SM", None)
         ref = sb.CacheTable(k, H, quant)
         ref.store(torch.from_numpy(x).to(DEV))
         assert torch.equal(tq.storage, ref.storage), quant
