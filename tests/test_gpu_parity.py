@@ -1004,7 +1004,7 @@ def test_projection_fold(Hf, H, k):
     P, bound = po.fold_projection(rows, W)
     perm = rng.permutation(k)
     import os
-    # both tensor-core paths: CTA pairs on one 256 x 256 tile (tcgen05.mma.cta_group::2; the default for FP32 / FP16 tables with
+    # both tensor-core paths: CTA pairs on one 256 x 256 tile (tcgen05.mma.cta_group::2; the default for FP16 tables with
     # K >= 512) and one 128 x 256 tile per CTA
     xs = {}
     for two_sm in ("0", "1"):
