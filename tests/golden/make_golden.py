@@ -13,6 +13,9 @@ What each fixture pins (reference file:line):
   fit_small.npz   fit (truncate-then-filter, tie order) on a seeded Zipf corpus,
                   longest match on a [B, L] batch incl. rows crossing nothing,
                   and the raw all-containing lists of get_token_f_grams
+  fit_medium.npz  fit on 300 texts / 60 k tokens with max_f_grams = 3000: the cut falls
+                  inside a run of equal counts (first-seen order decides), texts
+                  shorter than max_n (n_gram_extractor.py:58-70, :91-99)
   vocab_n5.npz    a max_n = 5 vocabulary WITHOUT unigrams (lengths 2..5, set
                   directly on the extractor the way NGramExtractor.load does,
                   n_gram_extractor.py:159-165), longest match on a batch
@@ -122,6 +125,24 @@ def make_fit_small():
                         cont_flat_offs=np.cumsum([0] + [len(f) for f in flat]).astype(np.int64))
 
 
+def make_fit_medium():
+    """A corpus large enough for the things fit_small cannot show: thousands of n-grams TIED at the truncation boundary (the
+    reference keeps first-seen order among equal counts: Counter.most_common is a stable sort) and texts shorter than max_n."""
+    rng = np.random.default_rng(4321)
+    V = 2000
+    lens_ = [int(x) for x in rng.integers(1, 400, size=300)]
+    lens_[7], lens_[8], lens_[9] = 1, 2, 3                      # shorter than max_n
+    corpus = [zipf_tokens(rng, n, V, a=1.05).tolist() for n in lens_]
+    max_n, min_freq, max_f = 4, 3, 3000
+    ex = NGramExtractor(max_n=max_n, min_freq=min_freq, max_f_grams=max_f).fit(corpus, verbose=False)
+    toks, lens = vocab_arrays(ex, max_n)
+    corpus_flat = np.concatenate([np.array(c, dtype=np.int32) for c in corpus])
+    corpus_offs = np.cumsum([0] + [len(c) for c in corpus]).astype(np.int64)
+    np.savez_compressed(os.path.join(HERE, "fit_medium.npz"), corpus_flat=corpus_flat, corpus_offs=corpus_offs,
+                        max_n=max_n, min_freq=min_freq, max_f_grams=max_f, vocab_tokens=toks, vocab_lens=lens)
+    return ex
+
+
 def make_vocab_n5():
     rng = np.random.default_rng(77)
     V, max_n, N = 300, 5, 1500
@@ -216,6 +237,7 @@ def make_cache_small():
 if __name__ == "__main__":
     make_kat0()
     make_fit_small()
+    make_fit_medium()
     make_vocab_n5()
     make_cache_small()
     for f in sorted(os.listdir(HERE)):

@@ -35,8 +35,10 @@ def test_kat0_fit_and_match():
     assert po.fit([[7, 8, 7, 8, 9]], 2, 2, 3) == [(7,), (8,), (7, 8)]
 
 
-def test_fit_small_matches_reference():
-    z = load_golden("fit_small.npz")
+@pytest.mark.parametrize("name", ["fit_small.npz", "fit_medium.npz"])
+def test_fit_small_matches_reference(name):
+    """fit_medium: the max_f_grams cut falls inside a run of 594 n-grams with count 3 (first-seen order keeps 583 of them)."""
+    z = load_golden(name)
     grams = po.fit(_corpus(z), int(z["max_n"]), int(z["min_freq"]), int(z["max_f_grams"]))
     expect = [tuple(int(t) for t in z["vocab_tokens"][i, :z["vocab_lens"][i]]) for i in range(len(z["vocab_lens"]))]
     assert grams == expect
